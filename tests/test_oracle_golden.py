@@ -1,0 +1,62 @@
+"""Pin the oracle (and the caller re-enactment) to the reference's own golden vectors:
+TreeDataLikelihoodTest.java:131-314 (ten values, 5 decimals) and the BEAGLE tiny test."""
+import numpy as np
+import pytest
+
+import helpers as H
+from beast_mcmc_b200 import treedatalikelihood as tdl
+
+
+def _fmt(x):
+    return f"{x:.5f}"
+
+
+@pytest.mark.parametrize("name", list(H.primate_cases().keys()))
+@pytest.mark.parametrize("traversal_flags", [tdl.FLAG_FRAMEWORK_CPU, 0])
+def test_primates_through_delegate(name, traversal_flags):
+    model, site, expected = H.primate_cases()[name]
+    delegate = tdl.BeagleDataLikelihoodDelegate(
+        H.primate_tree(), H.primate_patterns(), model, site,
+        H.oracle_factory(report_flags=traversal_flags),
+        useAmbiguities=False, rescalingScheme=tdl.PartialsRescalingScheme.DEFAULT,
+        delayRescalingUntilUnderflow=False)     # exactly the ctor arguments of the JUnit test
+    like = tdl.TreeDataLikelihood(delegate, H.primate_tree())
+    assert _fmt(like.getLogLikelihood()) == _fmt(expected)
+    # the DYNAMIC scheme with delay=false rescales on the very first evaluation
+    assert delegate.useScaleFactors
+
+
+def test_primates_unscaled_equals_scaled():
+    model, site, expected = H.primate_cases()["GTRGI"]
+    vals = []
+    for scheme, delay in [(tdl.PartialsRescalingScheme.NONE, True), (tdl.PartialsRescalingScheme.ALWAYS, False),
+                          (tdl.PartialsRescalingScheme.DYNAMIC, False)]:
+        for log_flag in (0, 1 << 10):
+            d = tdl.BeagleDataLikelihoodDelegate(H.primate_tree(), H.primate_patterns(), model, site,
+                                                 H.oracle_factory(extra_flags=log_flag), rescalingScheme=scheme,
+                                                 delayRescalingUntilUnderflow=delay)
+            vals.append(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood())
+    assert np.allclose(vals, vals[0], rtol=1e-13, atol=0)
+    assert _fmt(vals[0]) == _fmt(expected)
+
+
+def test_primates_ambiguities_as_partials():
+    from beast_mcmc_b200.evomodel import nucleotide_state_set
+    model, site, expected = H.primate_cases()["HKY85G"]
+    d = tdl.BeagleDataLikelihoodDelegate(H.primate_tree(), H.primate_patterns(), model, site, H.oracle_factory(),
+                                         useAmbiguities=True, stateSetFn=nucleotide_state_set)
+    assert _fmt(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood()) == _fmt(expected)
+
+
+def test_beagle_tiny_test():
+    tree, pats, model, site, expected = H.tiny_case()
+    d = tdl.BeagleDataLikelihoodDelegate(tree, pats, model, site, H.oracle_factory(),
+                                         rescalingScheme=tdl.PartialsRescalingScheme.NONE)
+    assert _fmt(tdl.TreeDataLikelihood(d, tree).getLogLikelihood()) == _fmt(expected)
+
+
+def test_jc69_eigenvalues_match_beagle_tiny_constants():
+    # BeagleFactory.main hard-codes Eval = {0, -4/3, -4/3, -4/3} for JC69
+    _, _, model, _, _ = H.tiny_case()
+    lam = np.sort(model.getEigenDecomposition().Eval)
+    assert np.allclose(lam, [-4 / 3, -4 / 3, -4 / 3, 0.0], atol=1e-14)
