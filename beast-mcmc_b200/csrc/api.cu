@@ -1,0 +1,983 @@
+// api.cu -- the C ABI of libhmsbeagle.so (declared in include/libhmsbeagle_b200.h).
+//
+// Host side of the engine: instance table, resource list, buffer bookkeeping, translation of the
+// caller's integer op tuples into device op records (with dependency-safe re-ordering and operand
+// stack-slot assignment), and stream-ordered launches.  Every entry point selects the instance's
+// device explicitly: JNI calls arrive from arbitrary pool threads (CompoundLikelihood.java:63-75).
+// There is NO CPU fallback: without a CUDA device beagleCreateInstance fails with
+// BEAGLE_ERROR_NO_RESOURCE.
+#include "../../include/libhmsbeagle_b200.h"
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+
+using namespace b200;
+
+namespace {
+
+std::mutex gMutex;
+std::vector<Instance*> gInstances;
+
+const long kSupportedFlags =
+    BEAGLE_FLAG_PRECISION_DOUBLE | BEAGLE_FLAG_COMPUTATION_SYNCH | BEAGLE_FLAG_EIGEN_REAL |
+    BEAGLE_FLAG_EIGEN_COMPLEX | BEAGLE_FLAG_SCALING_MANUAL | BEAGLE_FLAG_SCALING_DYNAMIC |
+    BEAGLE_FLAG_SCALERS_RAW | BEAGLE_FLAG_SCALERS_LOG | BEAGLE_FLAG_VECTOR_NONE | BEAGLE_FLAG_THREADING_NONE |
+    BEAGLE_FLAG_PROCESSOR_GPU | BEAGLE_FLAG_FRAMEWORK_CUDA | BEAGLE_FLAG_PARALLELOPS_GRID;
+
+int envInt(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+Instance* getInstance(int id) {
+    std::lock_guard<std::mutex> lock(gMutex);
+    if (id < 0 || id >= (int)gInstances.size()) return nullptr;
+    return gInstances[id];
+}
+
+#define GET_INSTANCE(in, id)                                            \
+    Instance* in = getInstance(id);                                     \
+    if (in == nullptr) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;      \
+    if (cudaSetDevice(in->device) != cudaSuccess) return BEAGLE_ERROR_GENERAL;
+
+#define CUDA_OK(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            if (getenv("B200_BEAGLE_DEBUG"))                                                 \
+                fprintf(stderr, "[b200-beagle] %s failed: %s (%s:%d)\n", #expr,              \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                        \
+            return e__ == cudaErrorMemoryAllocation ? BEAGLE_ERROR_OUT_OF_MEMORY             \
+                                                    : BEAGLE_ERROR_GENERAL;                  \
+        }                                                                                    \
+    } while (0)
+
+struct TimedScope {
+    Instance* in;
+    int cls;
+    cudaEvent_t a = nullptr, b = nullptr;
+    TimedScope(Instance* i, int c) : in(i), cls(c) {
+        if (in->timing) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, in->stream);
+        }
+    }
+    ~TimedScope() {
+        if (in->timing) {
+            cudaEventRecord(b, in->stream);
+            in->timed[cls].push_back({a, b});
+        }
+    }
+};
+
+// reserve `bytes` in the pinned ring, copy `src` into it and enqueue the H2D to the mirrored
+// device ring; returns the device address.  On wrap the stream is drained once.
+void* stage(Instance* in, const void* src, size_t bytes) {
+    size_t need = (bytes + 255) & ~size_t(255);
+    if (need > in->stageSize) return nullptr;
+    if (in->stagePos + need > in->stageSize) {
+        cudaStreamSynchronize(in->stream);
+        in->stagePos = 0;
+    }
+    char* h = in->hStage + in->stagePos;
+    char* d = in->dStage + in->stagePos;
+    memcpy(h, src, bytes);
+    if (cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, in->stream) != cudaSuccess) return nullptr;
+    in->stagePos += need;
+    return d;
+}
+
+// small parameter upload straight into its device home (category rates, frequencies, ...)
+int uploadSmall(Instance* in, void* dDst, const void* src, size_t bytes) {
+    size_t need = (bytes + 255) & ~size_t(255);
+    if (need > in->stageSize) return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (in->stagePos + need > in->stageSize) {
+        cudaStreamSynchronize(in->stream);
+        in->stagePos = 0;
+    }
+    char* h = in->hStage + in->stagePos;
+    memcpy(h, src, bytes);
+    in->stagePos += need;
+    CUDA_OK(cudaMemcpyAsync(dDst, h, bytes, cudaMemcpyHostToDevice, in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+// bump allocator over large slabs: per-buffer storage is handed out on first use
+void* slabAlloc(Instance* in, size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes > in->slabLeft) {
+        size_t slab = std::max(bytes * 64, size_t(64) << 20);
+        slab = std::min(slab, std::max(bytes, size_t(2) << 30));
+        void* p = nullptr;
+        if (cudaMalloc(&p, slab) != cudaSuccess) {
+            cudaGetLastError();
+            slab = bytes;
+            if (cudaMalloc(&p, slab) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        in->slabs.push_back(p);
+        in->slabCur = static_cast<char*>(p);
+        in->slabLeft = slab;
+    }
+    void* r = in->slabCur;
+    in->slabCur += bytes;
+    in->slabLeft -= bytes;
+    return r;
+}
+
+double* ensurePartials(Instance* in, int idx) {
+    if (in->partials[idx] == nullptr)
+        in->partials[idx] = static_cast<double*>(slabAlloc(in, in->partialsElems * sizeof(double)));
+    return in->partials[idx];
+}
+
+bool validRange(int idx, int n) { return idx >= 0 && idx < n; }
+
+void destroyInstance(Instance* in) {
+    cudaSetDevice(in->device);
+    if (in->stream) cudaStreamSynchronize(in->stream);
+    for (void* p : in->slabs) cudaFree(p);
+    cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dRates); cudaFree(in->dWeights);
+    cudaFree(in->dFreqs); cudaFree(in->dScale); cudaFree(in->dPatternWeights);
+    cudaFree(in->dPatternPartitions); cudaFree(in->dSite); cudaFree(in->dBlockSums); cudaFree(in->dOut);
+    cudaFree(in->dCounter); cudaFree(in->dStage);
+    if (in->hStage) cudaFreeHost(in->hStage);
+    if (in->hOut) cudaFreeHost(in->hOut);
+    for (int c = 0; c < T_CLASSES; ++c)
+        for (auto& ev : in->timed[c]) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (in->stream) cudaStreamDestroy(in->stream);
+    delete in;
+}
+
+// ---- resources ------------------------------------------------------------------------------
+std::vector<BeagleResource> gResources;
+std::vector<std::string> gResourceStrings;
+BeagleResourceList gResourceList = {nullptr, 0};
+std::once_flag gResourceOnce;
+
+void buildResources() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    gResourceStrings.reserve(2 * (n + 1));
+    gResourceStrings.push_back("CPU (host)");
+    gResourceStrings.push_back("no host implementation in this library | use a GPU resource (1..N)");
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) != cudaSuccess) { cudaGetLastError(); continue; }
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s", prop.name);
+        gResourceStrings.push_back(buf);
+        snprintf(buf, sizeof buf, "Global memory (MB): %zu | SMs: %d | compute capability: %d.%d | "
+                 "B200-native walk kernels (sm_100a), double precision",
+                 (size_t)(prop.totalGlobalMem >> 20), prop.multiProcessorCount, prop.major, prop.minor);
+        gResourceStrings.push_back(buf);
+    }
+    size_t count = gResourceStrings.size() / 2;
+    gResources.resize(count);
+    for (size_t r = 0; r < count; ++r) {
+        gResources[r].name = const_cast<char*>(gResourceStrings[2 * r].c_str());
+        gResources[r].description = const_cast<char*>(gResourceStrings[2 * r + 1].c_str());
+        gResources[r].supportFlags = (r == 0) ? (BEAGLE_FLAG_PROCESSOR_CPU | BEAGLE_FLAG_FRAMEWORK_CPU) : kSupportedFlags;
+        gResources[r].requiredFlags = (r == 0) ? BEAGLE_FLAG_FRAMEWORK_CPU : BEAGLE_FLAG_FRAMEWORK_CUDA;
+    }
+    gResourceList.list = gResources.data();
+    gResourceList.length = (int)count;
+}
+
+char gImplName[] = "B200-CUDA-Double";
+char gImplDesc[] = "sm_100a walk kernels: one launch per operation list, shared-memory operand stack";
+
+// ---- op planning ------------------------------------------------------------------------------
+struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; };
+
+// Dependency-safe re-ordering (Sethi-Ullman: deeper-need subtree first) so that the number of
+// simultaneously live intermediate results -- operand-stack slots -- is minimal, and slot
+// assignment.  Any topological order is valid because pattern columns never interact.
+void planOrder(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder, std::vector<int>& order) {
+    const int n = (int)ops.size();
+    order.resize(n);
+    for (int k = 0; k < n; ++k) order[k] = k;
+    if (!allowReorder || n < 3) return;
+    std::vector<int> writer(nBuffers, -1);
+    for (int k = 0; k < n; ++k) {
+        if (writer[ops[k].dest] >= 0) return;           // double write: keep the caller's order
+        writer[ops[k].dest] = k;
+    }
+    std::vector<int> ch0(n, -1), ch1(n, -1), consumed(n, 0), need(n, 1);
+    for (int k = 0; k < n; ++k) {
+        const int a = writer[ops[k].c1], b = writer[ops[k].c2];
+        if (a >= 0) { if (a >= k) return; ch0[k] = a; consumed[a]++; }
+        if (b >= 0 && ops[k].c2 != ops[k].c1) { if (b >= k) return; ch1[k] = b; consumed[b]++; }
+        // scale buffers: a later op reading a scale buffer written earlier keeps its relative order
+        // automatically when it is an ancestor; otherwise (never issued by BEAST) bail out.
+        int na = ch0[k] >= 0 ? need[ch0[k]] : 0, nb = ch1[k] >= 0 ? need[ch1[k]] : 0;
+        if (na < nb) std::swap(na, nb);
+        need[k] = std::max(1, std::max(na, nb + (nb > 0 ? 1 : 0)));
+        if (consumed[k] > 1) return;                    // DAG, not a forest: keep the caller's order
+    }
+    for (int k = 0; k < n; ++k) if (consumed[k] > 1) return;
+    std::vector<int> out;
+    out.reserve(n);
+    std::vector<char> seen(n, 0);
+    std::vector<std::pair<int, int>> stack;
+    for (int r = 0; r < n; ++r) {
+        if (consumed[r] != 0) continue;
+        stack.push_back({r, 0});
+        while (!stack.empty()) {
+            auto [k, stageNo] = stack.back();
+            stack.pop_back();
+            if (stageNo == 1) { out.push_back(k); continue; }
+            if (seen[k]) continue;
+            seen[k] = 1;
+            stack.push_back({k, 1});
+            int a = ch0[k], b = ch1[k];
+            int na = a >= 0 ? need[a] : -1, nb = b >= 0 ? need[b] : -1;
+            // the child pushed LAST is visited FIRST: visit the larger need first
+            if (na >= nb) { if (b >= 0) stack.push_back({b, 0}); if (a >= 0) stack.push_back({a, 0}); }
+            else          { if (a >= 0) stack.push_back({a, 0}); if (b >= 0) stack.push_back({b, 0}); }
+        }
+    }
+    if ((int)out.size() == n) order.swap(out);
+}
+
+int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartition) {
+    const int n = (int)hops.size();
+    if (n == 0) return BEAGLE_SUCCESS;
+    // ---- validation + lazy allocation
+    for (const HostOp& o : hops) {
+        if (!validRange(o.dest, in->nBuffers) || !validRange(o.c1, in->nBuffers) ||
+            !validRange(o.c2, in->nBuffers) || !validRange(o.m1, in->nMatrices) ||
+            !validRange(o.m2, in->nMatrices))
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (o.sw != BEAGLE_OP_NONE && !validRange(o.sw, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (o.sr != BEAGLE_OP_NONE && !validRange(o.sr, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (o.cum != BEAGLE_OP_NONE && !validRange(o.cum, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (byPartition && !validRange(o.part, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (ensurePartials(in, o.dest) == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+        in->states8[o.dest] = nullptr;      // a written buffer holds partials from now on
+        in->states32[o.dest] = nullptr;
+    }
+    for (const HostOp& o : hops) {
+        if (in->partials[o.c1] == nullptr && in->states32[o.c1] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (in->partials[o.c2] == nullptr && in->states32[o.c2] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+    }
+    const bool fourState = in->Sp == 4;
+    std::vector<int> order;
+    planOrder(hops, in->nBuffers, in->reorder && !byPartition, order);
+
+    // ---- stack slots (4-state path only): one backward pass finds, for every produced value, the
+    // position of its LAST reader inside this list (before the buffer is re-written); the forward
+    // pass then parks results in slots and frees each slot at that last read.
+    const int maxDepth = (fourState && !byPartition && in->walkVariant >= 1) ? envInt("B200_STACK_DEPTH", 12) : 0;
+    std::vector<int> lastReadOfProd(maxDepth > 0 ? n : 0, -1);
+    if (maxDepth > 0) {
+        std::vector<int> lastRead(in->nBuffers, -1);
+        for (int pos = n - 1; pos >= 0; --pos) {
+            const HostOp& o = hops[order[pos]];
+            lastReadOfProd[pos] = lastRead[o.dest];
+            lastRead[o.dest] = -1;
+            if (lastRead[o.c1] < 0) lastRead[o.c1] = pos;
+            if (lastRead[o.c2] < 0) lastRead[o.c2] = pos;
+        }
+    }
+    std::vector<int> slotOf(maxDepth > 0 ? in->nBuffers : 0, -1), slotFreeAt(maxDepth > 0 ? in->nBuffers : 0, -1);
+    std::vector<int> freeSlots;
+    int depthUsed = 0;
+
+    std::vector<DevOp> dops(n);
+    for (int pos = 0; pos < n; ++pos) {
+        const HostOp& o = hops[order[pos]];
+        DevOp& d = dops[pos];
+        memset(&d, 0, sizeof d);
+        d.dest = in->partials[o.dest];
+        const bool t1 = in->states32[o.c1] != nullptr && in->partials[o.c1] == nullptr;
+        const bool t2 = in->states32[o.c2] != nullptr && in->partials[o.c2] == nullptr;
+        d.c1 = t1 ? nullptr : in->partials[o.c1];
+        d.c2 = t2 ? nullptr : in->partials[o.c2];
+        d.s1 = t1 ? (fourState ? (const void*)in->states8[o.c1] : (const void*)in->states32[o.c1]) : nullptr;
+        d.s2 = t2 ? (fourState ? (const void*)in->states8[o.c2] : (const void*)in->states32[o.c2]) : nullptr;
+        d.m1 = in->dMat + (size_t)o.m1 * in->C * in->Sp * in->Sp;
+        d.m2 = in->dMat + (size_t)o.m2 * in->C * in->Sp * in->Sp;
+        d.scaleWrite = o.sw >= 0 ? in->dScale + (size_t)o.sw * in->Ppad : nullptr;
+        d.scaleRead = o.sr >= 0 ? in->dScale + (size_t)o.sr * in->Ppad : nullptr;
+        d.cumScale = (o.cum >= 0 && o.sw >= 0) ? in->dScale + (size_t)o.cum * in->Ppad : nullptr;
+        if (byPartition) { d.pBegin = in->partBegin[o.part]; d.pEnd = in->partEnd[o.part]; }
+        else { d.pBegin = 0; d.pEnd = in->P; }
+        d.srcSlot1 = d.srcSlot2 = d.dstSlot = -1;
+        if (maxDepth > 0) {
+            auto take = [&](int buf, bool isTip) -> int {
+                if (isTip) return -1;
+                const int slot = slotOf[buf];
+                if (slot >= 0 && slotFreeAt[buf] == pos) { freeSlots.push_back(slot); slotOf[buf] = -1; }
+                return slot;
+            };
+            d.srcSlot1 = take(o.c1, t1);
+            d.srcSlot2 = (o.c2 == o.c1) ? d.srcSlot1 : take(o.c2, t2);
+            if (slotOf[o.dest] >= 0) { freeSlots.push_back(slotOf[o.dest]); slotOf[o.dest] = -1; }   // stale value
+            if (lastReadOfProd[pos] > pos) {         // a later op of this list reads the result
+                int slot = -1;
+                if (!freeSlots.empty()) { slot = freeSlots.back(); freeSlots.pop_back(); }
+                else if (depthUsed < maxDepth) slot = depthUsed++;
+                if (slot >= 0) { slotOf[o.dest] = slot; slotFreeAt[o.dest] = lastReadOfProd[pos]; d.dstSlot = slot; }
+            }
+        }
+    }
+    void* dOps = stage(in, dops.data(), sizeof(DevOp) * n);
+    if (dOps == nullptr) {
+        // list larger than the ring: fall back to a one-off allocation
+        void* tmp = nullptr;
+        CUDA_OK(cudaMalloc(&tmp, sizeof(DevOp) * n));
+        CUDA_OK(cudaMemcpyAsync(tmp, dops.data(), sizeof(DevOp) * n, cudaMemcpyHostToDevice, in->stream));
+        CUDA_OK(cudaStreamSynchronize(in->stream));
+        cudaError_t e;
+        {
+            TimedScope ts(in, T_PARTIALS);
+            e = fourState ? launchWalk4(in, static_cast<DevOp*>(tmp), n, depthUsed)
+                          : launchWalkGeneric(in, static_cast<DevOp*>(tmp), n);
+        }
+        cudaStreamSynchronize(in->stream);
+        cudaFree(tmp);
+        CUDA_OK(e);
+        return BEAGLE_SUCCESS;
+    }
+    {
+        TimedScope ts(in, T_PARTIALS);
+        CUDA_OK(fourState ? launchWalk4(in, static_cast<DevOp*>(dOps), n, depthUsed)
+                          : launchWalkGeneric(in, static_cast<DevOp*>(dOps), n));
+    }
+    return BEAGLE_SUCCESS;
+}
+
+}  // namespace
+
+// ==============================================================================================
+// exported C ABI
+// ==============================================================================================
+extern "C" {
+
+const char* beagleGetVersion(void) { return "4.0.1-b200"; }
+
+const char* beagleGetCitation(void) {
+    return "B200-native tree-likelihood engine exposing the BEAGLE API.\n"
+           "API after: Ayres et al. (2019) BEAGLE 3. Syst Biol 68:1052-1061.";
+}
+
+BeagleResourceList* beagleGetResourceList(void) {
+    std::call_once(gResourceOnce, buildResources);
+    return &gResourceList;
+}
+
+BeagleBenchmarkedResourceList* beagleGetBenchmarkedResourceList(int, int, int, int, int, int*, int, long, long, int,
+                                                                int, int, long) {
+    return nullptr;   // -beagle_auto benchmarking: not implemented this round
+}
+
+int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBufferCount, int stateCount,
+                         int patternCount, int eigenBufferCount, int matrixBufferCount, int categoryCount,
+                         int scaleBufferCount, int* resourceList, int resourceCount, long preferenceFlags,
+                         long requirementFlags, BeagleInstanceDetails* returnInfo) {
+    if (tipCount < 0 || partialsBufferCount < 0 || compactBufferCount < 0 || stateCount < 2 ||
+        patternCount < 1 || eigenBufferCount < 0 || matrixBufferCount < 0 || categoryCount < 1 ||
+        scaleBufferCount < 0 || stateCount > 255)
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (requirementFlags & ~kSupportedFlags) return BEAGLE_ERROR_NO_RESOURCE;
+    BeagleResourceList* rl = beagleGetResourceList();
+    int resource = -1;
+    if (resourceList == nullptr || resourceCount <= 0) {
+        if (rl->length > 1) resource = 1;
+    } else {
+        for (int k = 0; k < resourceCount; ++k)
+            if (resourceList[k] >= 1 && resourceList[k] < rl->length) { resource = resourceList[k]; break; }
+    }
+    if (resource < 1) return BEAGLE_ERROR_NO_RESOURCE;   // no CUDA device, or only resource 0 requested
+
+    Instance* in = new Instance();
+    in->device = resource - 1;
+    in->resource = resource;
+    if (cudaSetDevice(in->device) != cudaSuccess) { delete in; return BEAGLE_ERROR_NO_RESOURCE; }
+    in->tipCount = tipCount; in->nPartials = partialsBufferCount; in->nCompact = compactBufferCount;
+    in->S = stateCount; in->P = patternCount; in->nEigen = eigenBufferCount; in->nMatrices = matrixBufferCount;
+    in->C = categoryCount; in->nScale = scaleBufferCount;
+    in->Sp = stateCount <= 4 ? 4 : ((stateCount + 3) / 4) * 4;
+    in->Ppad = ((patternCount + 31) / 32) * 32;
+    in->nBuffers = partialsBufferCount + compactBufferCount;
+    in->nSets = std::max(1, eigenBufferCount);
+    in->complexEigen = (requirementFlags | preferenceFlags) & BEAGLE_FLAG_EIGEN_COMPLEX;
+    in->logScalers = (requirementFlags | preferenceFlags) & BEAGLE_FLAG_SCALERS_LOG;
+    in->flags = BEAGLE_FLAG_PRECISION_DOUBLE | BEAGLE_FLAG_COMPUTATION_SYNCH | BEAGLE_FLAG_SCALING_MANUAL |
+                BEAGLE_FLAG_VECTOR_NONE | BEAGLE_FLAG_THREADING_NONE | BEAGLE_FLAG_PROCESSOR_GPU |
+                BEAGLE_FLAG_FRAMEWORK_CUDA | BEAGLE_FLAG_PARALLELOPS_GRID |
+                (in->complexEigen ? BEAGLE_FLAG_EIGEN_COMPLEX : BEAGLE_FLAG_EIGEN_REAL) |
+                (in->logScalers ? BEAGLE_FLAG_SCALERS_LOG : BEAGLE_FLAG_SCALERS_RAW);
+    if ((requirementFlags | preferenceFlags) & BEAGLE_FLAG_SCALING_DYNAMIC) {
+        in->flags &= ~BEAGLE_FLAG_SCALING_MANUAL;
+        in->flags |= BEAGLE_FLAG_SCALING_DYNAMIC;
+    }
+    in->partialsElems = (size_t)in->C * in->Ppad * in->Sp;
+    in->partials.assign(in->nBuffers, nullptr);
+    in->states8.assign(in->nBuffers, nullptr);
+    in->states32.assign(in->nBuffers, nullptr);
+    in->walkBlock = envInt("B200_WALK_BLOCK", 128);
+    if (in->walkBlock < 32 || in->walkBlock > 256 || (in->walkBlock & 31)) in->walkBlock = 128;
+    in->walkVariant = envInt("B200_WALK_VARIANT", 1);
+    in->reorder = envInt("B200_REORDER", 1);
+
+    cudaDeviceProp prop;
+    bool ok = cudaGetDeviceProperties(&prop, in->device) == cudaSuccess;
+    if (ok) { in->smCount = prop.multiProcessorCount; in->maxSmemOptin = prop.sharedMemPerBlockOptin; }
+    ok = ok && cudaStreamCreateWithFlags(&in->stream, cudaStreamNonBlocking) == cudaSuccess;
+    const size_t eigenStride = 2 * (size_t)in->S * in->S + 2 * in->S;
+    const size_t matElems = (size_t)in->nMatrices * in->C * in->Sp * in->Sp;
+    const int rootBlocks = (in->Ppad + 255) / 256;
+    in->stageSize = size_t(8) << 20;
+    auto alloc = [&](auto** p, size_t elems) {
+        if (!ok) return;
+        using T = std::remove_pointer_t<std::remove_pointer_t<decltype(p)>>;
+        size_t bytes = std::max<size_t>(elems, 1) * sizeof(T);
+        ok = cudaMalloc(reinterpret_cast<void**>(p), bytes) == cudaSuccess &&
+             cudaMemsetAsync(*p, 0, bytes, in->stream) == cudaSuccess;
+    };
+    alloc(&in->dEigen, std::max(1, in->nEigen) * eigenStride);
+    alloc(&in->dMat, matElems);
+    alloc(&in->dRates, (size_t)in->nSets * in->C);
+    alloc(&in->dWeights, (size_t)in->nSets * in->C);
+    alloc(&in->dFreqs, (size_t)in->nSets * in->Sp);
+    alloc(&in->dScale, (size_t)in->nScale * in->Ppad);
+    alloc(&in->dPatternWeights, in->Ppad);
+    alloc(&in->dPatternPartitions, in->Ppad);
+    alloc(&in->dSite, in->Ppad);
+    alloc(&in->dBlockSums, rootBlocks);
+    alloc(&in->dOut, 1024);
+    alloc(&in->dCounter, 4);
+    alloc(&in->dStage, in->stageSize);
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&in->hStage), in->stageSize) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&in->hOut), 1024 * sizeof(double)) == cudaSuccess;
+    if (ok) {
+        // default: one rate category set of all ones, unit pattern weights (upstream defaults)
+        std::vector<double> ones((size_t)std::max(in->nSets * in->C, in->Ppad), 1.0);
+        ok = cudaMemcpyAsync(in->dRates, ones.data(), sizeof(double) * in->nSets * in->C, cudaMemcpyHostToDevice,
+                             in->stream) == cudaSuccess;
+        std::vector<double> w(in->Ppad, 0.0);
+        std::fill(w.begin(), w.begin() + in->P, 1.0);
+        ok = ok && cudaMemcpyAsync(in->dPatternWeights, w.data(), sizeof(double) * in->Ppad, cudaMemcpyHostToDevice,
+                                   in->stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(in->stream) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaError_t e = cudaGetLastError();
+        destroyInstance(in);
+        return e == cudaErrorMemoryAllocation ? BEAGLE_ERROR_OUT_OF_MEMORY : BEAGLE_ERROR_GENERAL;
+    }
+    in->partitionCount = 1;
+    in->partBegin.assign(1, 0);
+    in->partEnd.assign(1, in->P);
+    {
+        std::lock_guard<std::mutex> lock(gMutex);
+        int id = -1;
+        for (size_t k = 0; k < gInstances.size(); ++k) if (gInstances[k] == nullptr) { id = (int)k; break; }
+        if (id < 0) { gInstances.push_back(nullptr); id = (int)gInstances.size() - 1; }
+        gInstances[id] = in;
+        in->id = id;
+    }
+    if (returnInfo != nullptr) {
+        returnInfo->resourceNumber = resource;
+        returnInfo->resourceName = rl->list[resource].name;
+        returnInfo->implName = gImplName;
+        returnInfo->implDescription = gImplDesc;
+        returnInfo->flags = in->flags;
+    }
+    return in->id;
+}
+
+int beagleFinalizeInstance(int instance) {
+    Instance* in = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(gMutex);
+        if (instance < 0 || instance >= (int)gInstances.size() || gInstances[instance] == nullptr)
+            return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
+        in = gInstances[instance];
+        gInstances[instance] = nullptr;
+    }
+    destroyInstance(in);
+    return BEAGLE_SUCCESS;
+}
+
+int beagleFinalize(void) {
+    std::vector<Instance*> all;
+    {
+        std::lock_guard<std::mutex> lock(gMutex);
+        all.swap(gInstances);
+    }
+    for (Instance* in : all) if (in) destroyInstance(in);
+    return BEAGLE_SUCCESS;
+}
+
+int beagleSetCPUThreadCount(int instance, int) {
+    GET_INSTANCE(in, instance);
+    (void)in;
+    return BEAGLE_SUCCESS;
+}
+
+// ---- data upload ------------------------------------------------------------------------------
+int beagleSetTipStates(int instance, int tipIndex, const int* inStates) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(tipIndex, in->nBuffers) || inStates == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<int> s32(in->Ppad, in->S);
+    std::vector<uint8_t> s8(in->Ppad, (uint8_t)in->S);
+    for (int p = 0; p < in->P; ++p) {
+        int s = inStates[p];
+        if (s < 0 || s >= in->S) s = in->S;
+        s32[p] = s;
+        s8[p] = (uint8_t)s;
+    }
+    if (in->states32[tipIndex] == nullptr) {
+        in->states32[tipIndex] = static_cast<int*>(slabAlloc(in, sizeof(int) * in->Ppad));
+        in->states8[tipIndex] = static_cast<uint8_t*>(slabAlloc(in, in->Ppad));
+        if (in->states32[tipIndex] == nullptr || in->states8[tipIndex] == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+    }
+    CUDA_OK(cudaMemcpyAsync(in->states32[tipIndex], s32.data(), sizeof(int) * in->Ppad, cudaMemcpyHostToDevice, in->stream));
+    CUDA_OK(cudaMemcpyAsync(in->states8[tipIndex], s8.data(), in->Ppad, cudaMemcpyHostToDevice, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    in->partials[tipIndex] = nullptr;       // the buffer is a compact tip from now on
+    return BEAGLE_SUCCESS;
+}
+
+int beagleGetTipStates(int instance, int tipIndex, int* outStates) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(tipIndex, in->nBuffers) || in->states32[tipIndex] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+    CUDA_OK(cudaMemcpyAsync(outStates, in->states32[tipIndex], sizeof(int) * in->P, cudaMemcpyDeviceToHost, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+static int setPartialsImpl(Instance* in, int bufferIndex, const double* inPartials, bool perCategory) {
+    if (!validRange(bufferIndex, in->nBuffers) || inPartials == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+    double* dst = ensurePartials(in, bufferIndex);
+    if (dst == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+    std::vector<double> tmp(in->partialsElems, 0.0);
+    for (int c = 0; c < in->C; ++c)
+        for (int p = 0; p < in->Ppad; ++p) {
+            double* row = tmp.data() + ((size_t)c * in->Ppad + p) * in->Sp;
+            if (p < in->P) {
+                const double* src = inPartials + ((size_t)(perCategory ? c : 0) * in->P + p) * in->S;
+                for (int i = 0; i < in->S; ++i) row[i] = src[i];
+            } else {
+                for (int i = 0; i < in->S; ++i) row[i] = 1.0;     // padded patterns: harmless, finite
+            }
+        }
+    CUDA_OK(cudaMemcpyAsync(dst, tmp.data(), sizeof(double) * in->partialsElems, cudaMemcpyHostToDevice, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    in->states32[bufferIndex] = nullptr;
+    in->states8[bufferIndex] = nullptr;
+    return BEAGLE_SUCCESS;
+}
+
+int beagleSetTipPartials(int instance, int tipIndex, const double* inPartials) {
+    GET_INSTANCE(in, instance);
+    return setPartialsImpl(in, tipIndex, inPartials, false);
+}
+
+int beagleSetPartials(int instance, int bufferIndex, const double* inPartials) {
+    GET_INSTANCE(in, instance);
+    return setPartialsImpl(in, bufferIndex, inPartials, true);
+}
+
+int beagleGetPartials(int instance, int bufferIndex, int scaleIndex, double* outPartials) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(bufferIndex, in->nBuffers) || in->partials[bufferIndex] == nullptr || outPartials == nullptr)
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (scaleIndex != BEAGLE_OP_NONE && !validRange(scaleIndex, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<double> tmp(in->partialsElems);
+    const double* src = in->partials[bufferIndex];
+    double* dTmp = nullptr;
+    if (scaleIndex != BEAGLE_OP_NONE) {
+        CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dTmp), sizeof(double) * in->partialsElems));
+        CUDA_OK(cudaMemcpyAsync(dTmp, src, sizeof(double) * in->partialsElems, cudaMemcpyDeviceToDevice, in->stream));
+        CUDA_OK(launchRescalePartialsForGet(in, dTmp, in->dScale + (size_t)scaleIndex * in->Ppad));
+        src = dTmp;
+    }
+    cudaError_t e = cudaMemcpyAsync(tmp.data(), src, sizeof(double) * in->partialsElems, cudaMemcpyDeviceToHost, in->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(in->stream);
+    if (dTmp) cudaFree(dTmp);
+    CUDA_OK(e);
+    for (int c = 0; c < in->C; ++c)
+        for (int p = 0; p < in->P; ++p)
+            memcpy(outPartials + ((size_t)c * in->P + p) * in->S, tmp.data() + ((size_t)c * in->Ppad + p) * in->Sp,
+                   sizeof(double) * in->S);
+    return BEAGLE_SUCCESS;
+}
+
+int beagleSetEigenDecomposition(int instance, int eigenIndex, const double* inEigenVectors,
+                                const double* inInverseEigenVectors, const double* inEigenValues) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(eigenIndex, in->nEigen)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    const size_t S = in->S, stride = 2 * S * S + 2 * S;
+    std::vector<double> pack(stride, 0.0);
+    memcpy(pack.data(), inEigenVectors, sizeof(double) * S * S);
+    memcpy(pack.data() + S * S, inInverseEigenVectors, sizeof(double) * S * S);
+    memcpy(pack.data() + 2 * S * S, inEigenValues, sizeof(double) * (in->complexEigen ? 2 * S : S));
+    return uploadSmall(in, in->dEigen + (size_t)eigenIndex * stride, pack.data(), sizeof(double) * stride);
+}
+
+int beagleSetStateFrequencies(int instance, int stateFrequenciesIndex, const double* inStateFrequencies) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(stateFrequenciesIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<double> f(in->Sp, 0.0);
+    memcpy(f.data(), inStateFrequencies, sizeof(double) * in->S);
+    return uploadSmall(in, in->dFreqs + (size_t)stateFrequenciesIndex * in->Sp, f.data(), sizeof(double) * in->Sp);
+}
+
+int beagleSetCategoryWeights(int instance, int categoryWeightsIndex, const double* inCategoryWeights) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(categoryWeightsIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return uploadSmall(in, in->dWeights + (size_t)categoryWeightsIndex * in->C, inCategoryWeights, sizeof(double) * in->C);
+}
+
+int beagleSetCategoryRatesWithIndex(int instance, int categoryRatesIndex, const double* inCategoryRates) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(categoryRatesIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return uploadSmall(in, in->dRates + (size_t)categoryRatesIndex * in->C, inCategoryRates, sizeof(double) * in->C);
+}
+
+int beagleSetCategoryRates(int instance, const double* inCategoryRates) {
+    return beagleSetCategoryRatesWithIndex(instance, 0, inCategoryRates);
+}
+
+int beagleSetPatternWeights(int instance, const double* inPatternWeights) {
+    GET_INSTANCE(in, instance);
+    std::vector<double> w(in->Ppad, 0.0);
+    memcpy(w.data(), inPatternWeights, sizeof(double) * in->P);
+    CUDA_OK(cudaMemcpyAsync(in->dPatternWeights, w.data(), sizeof(double) * in->Ppad, cudaMemcpyHostToDevice, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleSetPatternPartitions(int instance, int partitionCount, const int* inPatternPartitions) {
+    GET_INSTANCE(in, instance);
+    if (partitionCount < 1 || partitionCount > 1000) return BEAGLE_ERROR_OUT_OF_RANGE;
+    // contiguous, non-decreasing maps only -- what MPDLD:520-533 builds
+    std::vector<int> begin(partitionCount, 0), end(partitionCount, 0);
+    int prev = -1;
+    for (int p = 0; p < in->P; ++p) {
+        int k = inPatternPartitions[p];
+        if (k < 0 || k >= partitionCount) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (k < prev) return BEAGLE_ERROR_NO_IMPLEMENTATION;
+        if (k != prev) { for (int q = prev + 1; q <= k; ++q) begin[q] = end[q] = p; prev = k; }
+        end[k] = p + 1;
+    }
+    for (int q = prev + 1; q < partitionCount; ++q) begin[q] = end[q] = in->P;
+    in->partitionCount = partitionCount;
+    in->partBegin = begin;
+    in->partEnd = end;
+    in->hostPartitions.assign(inPatternPartitions, inPatternPartitions + in->P);
+    return BEAGLE_SUCCESS;
+}
+
+// ---- transition matrices ----------------------------------------------------------------------
+static int updateMatricesImpl(Instance* in, const int* eigenIndices, int eigenIndexScalar, const int* rateSets,
+                              const int* probabilityIndices, const double* edgeLengths, int count) {
+    if (count <= 0) return BEAGLE_SUCCESS;
+    std::vector<int> pack(3 * (size_t)count);
+    for (int k = 0; k < count; ++k) {
+        int e = eigenIndices ? eigenIndices[k] : eigenIndexScalar;
+        int r = rateSets ? rateSets[k] : 0;
+        if (!validRange(probabilityIndices[k], in->nMatrices) || !validRange(e, in->nEigen) ||
+            !validRange(r, in->nSets))
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        pack[k] = probabilityIndices[k];
+        pack[count + k] = e;
+        pack[2 * (size_t)count + k] = r;
+    }
+    int* dIdx = static_cast<int*>(stage(in, pack.data(), sizeof(int) * pack.size()));
+    double* dLen = static_cast<double*>(stage(in, edgeLengths, sizeof(double) * count));
+    if (dIdx == nullptr || dLen == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+    TimedScope ts(in, T_MATRICES);
+    CUDA_OK(launchTransitionMatrices(in, dIdx, dIdx + count, dIdx + 2 * (size_t)count, dLen, count));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleUpdateTransitionMatrices(int instance, int eigenIndex, const int* probabilityIndices,
+                                   const int* firstDerivativeIndices, const int* secondDerivativeIndices,
+                                   const double* edgeLengths, int count) {
+    GET_INSTANCE(in, instance);
+    if (firstDerivativeIndices != nullptr || secondDerivativeIndices != nullptr)
+        return BEAGLE_ERROR_NO_IMPLEMENTATION;      // derivative matrices: SURVEY.md 8f "next"
+    return updateMatricesImpl(in, nullptr, eigenIndex, nullptr, probabilityIndices, edgeLengths, count);
+}
+
+int beagleUpdateTransitionMatricesWithMultipleModels(int instance, const int* eigenIndices,
+                                                     const int* categoryRateIndices, const int* probabilityIndices,
+                                                     const int* firstDerivativeIndices,
+                                                     const int* secondDerivativeIndices, const double* edgeLengths,
+                                                     int count) {
+    GET_INSTANCE(in, instance);
+    if (firstDerivativeIndices != nullptr || secondDerivativeIndices != nullptr)
+        return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    return updateMatricesImpl(in, eigenIndices, 0, categoryRateIndices, probabilityIndices, edgeLengths, count);
+}
+
+int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMatrix, double) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(matrixIndex, in->nMatrices)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    const size_t n = (size_t)in->C * in->Sp * in->Sp;
+    std::vector<double> t(n, 0.0);
+    for (int c = 0; c < in->C; ++c)
+        for (int i = 0; i < in->S; ++i)
+            for (int j = 0; j < in->S; ++j)
+                t[((size_t)c * in->Sp + j) * in->Sp + i] = inMatrix[((size_t)c * in->S + i) * in->S + j];
+    CUDA_OK(cudaMemcpyAsync(in->dMat + matrixIndex * n, t.data(), sizeof(double) * n, cudaMemcpyHostToDevice, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleGetTransitionMatrix(int instance, int matrixIndex, double* outMatrix) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(matrixIndex, in->nMatrices)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    const size_t n = (size_t)in->C * in->Sp * in->Sp;
+    std::vector<double> t(n);
+    CUDA_OK(cudaMemcpyAsync(t.data(), in->dMat + matrixIndex * n, sizeof(double) * n, cudaMemcpyDeviceToHost, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    for (int c = 0; c < in->C; ++c)
+        for (int i = 0; i < in->S; ++i)
+            for (int j = 0; j < in->S; ++j)
+                outMatrix[((size_t)c * in->S + i) * in->S + j] = t[((size_t)c * in->Sp + j) * in->Sp + i];
+    return BEAGLE_SUCCESS;
+}
+
+int beagleSetDifferentialMatrix(int, int, const double*) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+int beagleConvolveTransitionMatrices(int, const int*, const int*, const int*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+int beagleAddTransitionMatrices(int, const int*, const int*, const int*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+int beagleTransposeTransitionMatrices(int, const int*, const int*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+
+// ---- partials ---------------------------------------------------------------------------------
+int beagleUpdatePartials(int instance, const BeagleOperation* operations, int operationCount,
+                         int cumulativeScaleIndex) {
+    GET_INSTANCE(in, instance);
+    if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<HostOp> hops(operationCount);
+    for (int k = 0; k < operationCount; ++k) {
+        const BeagleOperation& o = operations[k];
+        hops[k] = {o.destinationPartials, o.destinationScaleWrite, o.destinationScaleRead, o.child1Partials,
+                   o.child1TransitionMatrix, o.child2Partials, o.child2TransitionMatrix, 0, cumulativeScaleIndex};
+    }
+    return planAndLaunch(in, hops, false);
+}
+
+int beagleUpdatePartialsByPartition(int instance, const BeagleOperationByPartition* operations, int operationCount) {
+    GET_INSTANCE(in, instance);
+    if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<HostOp> hops(operationCount);
+    for (int k = 0; k < operationCount; ++k) {
+        const BeagleOperationByPartition& o = operations[k];
+        hops[k] = {o.destinationPartials, o.destinationScaleWrite, o.destinationScaleRead, o.child1Partials,
+                   o.child1TransitionMatrix, o.child2Partials, o.child2TransitionMatrix, o.partition,
+                   o.cumulativeScaleIndex};
+    }
+    return planAndLaunch(in, hops, true);
+}
+
+int beagleWaitForPartials(int instance, const int*, int) {
+    GET_INSTANCE(in, instance);
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleUpdatePrePartials(int, const BeagleOperation*, int, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+int beagleUpdatePrePartialsByPartition(int, const BeagleOperationByPartition*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+
+// ---- scale factors ----------------------------------------------------------------------------
+static int accumulateImpl(Instance* in, const int* scaleIndices, int count, int cum, double sign, int pBegin, int pEnd) {
+    if (!validRange(cum, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (count <= 0) return BEAGLE_SUCCESS;
+    for (int k = 0; k < count; ++k) if (!validRange(scaleIndices[k], in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    int* dIdx = static_cast<int*>(stage(in, scaleIndices, sizeof(int) * count));
+    if (dIdx == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+    TimedScope ts(in, T_ROOT);
+    CUDA_OK(launchScaleAccumulate(in, dIdx, count, in->dScale + (size_t)cum * in->Ppad, sign, pBegin, pEnd));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleAccumulateScaleFactors(int instance, const int* scaleIndices, int count, int cumulativeScaleIndex) {
+    GET_INSTANCE(in, instance);
+    return accumulateImpl(in, scaleIndices, count, cumulativeScaleIndex, 1.0, 0, in->P);
+}
+
+int beagleAccumulateScaleFactorsByPartition(int instance, const int* scaleIndices, int count,
+                                            int cumulativeScaleIndex, int partitionIndex) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(partitionIndex, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return accumulateImpl(in, scaleIndices, count, cumulativeScaleIndex, 1.0, in->partBegin[partitionIndex],
+                          in->partEnd[partitionIndex]);
+}
+
+int beagleRemoveScaleFactors(int instance, const int* scaleIndices, int count, int cumulativeScaleIndex) {
+    GET_INSTANCE(in, instance);
+    return accumulateImpl(in, scaleIndices, count, cumulativeScaleIndex, -1.0, 0, in->P);
+}
+
+int beagleRemoveScaleFactorsByPartition(int instance, const int* scaleIndices, int count, int cumulativeScaleIndex,
+                                        int partitionIndex) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(partitionIndex, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return accumulateImpl(in, scaleIndices, count, cumulativeScaleIndex, -1.0, in->partBegin[partitionIndex],
+                          in->partEnd[partitionIndex]);
+}
+
+int beagleResetScaleFactors(int instance, int cumulativeScaleIndex) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(cumulativeScaleIndex, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    CUDA_OK(cudaMemsetAsync(in->dScale + (size_t)cumulativeScaleIndex * in->Ppad, 0, sizeof(double) * in->Ppad, in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleResetScaleFactorsByPartition(int instance, int cumulativeScaleIndex, int partitionIndex) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(cumulativeScaleIndex, in->nScale) || !validRange(partitionIndex, in->partitionCount))
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    int b = in->partBegin[partitionIndex], e = in->partEnd[partitionIndex];
+    if (e > b)
+        CUDA_OK(cudaMemsetAsync(in->dScale + (size_t)cumulativeScaleIndex * in->Ppad + b, 0, sizeof(double) * (e - b), in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleCopyScaleFactors(int instance, int destScalingIndex, int srcScalingIndex) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(destScalingIndex, in->nScale) || !validRange(srcScalingIndex, in->nScale))
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    CUDA_OK(cudaMemcpyAsync(in->dScale + (size_t)destScalingIndex * in->Ppad, in->dScale + (size_t)srcScalingIndex * in->Ppad,
+                            sizeof(double) * in->Ppad, cudaMemcpyDeviceToDevice, in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleGetScaleFactors(int instance, int srcScalingIndex, double* outScaleFactors) {
+    GET_INSTANCE(in, instance);
+    if (!validRange(srcScalingIndex, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    CUDA_OK(cudaMemcpyAsync(outScaleFactors, in->dScale + (size_t)srcScalingIndex * in->Ppad, sizeof(double) * in->P,
+                            cudaMemcpyDeviceToHost, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleGetLogScaleFactors(int instance, int srcScalingIndex, double* outLogScaleFactors) {
+    int rc = beagleGetScaleFactors(instance, srcScalingIndex, outLogScaleFactors);
+    if (rc != BEAGLE_SUCCESS) return rc;
+    Instance* in = getInstance(instance);
+    if (!in->logScalers)
+        for (int p = 0; p < in->P; ++p) outLogScaleFactors[p] = log(outLogScaleFactors[p]);
+    return BEAGLE_SUCCESS;
+}
+
+// ---- root -------------------------------------------------------------------------------------
+static int rootLaunch(Instance* in, int buffer, int wIdx, int fIdx, int cum, int pBegin, int pEnd, double* dOutSlot) {
+    if (!validRange(buffer, in->nBuffers) || in->partials[buffer] == nullptr || !validRange(wIdx, in->nSets) ||
+        !validRange(fIdx, in->nSets))
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (cum != BEAGLE_OP_NONE && !validRange(cum, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    TimedScope ts(in, T_ROOT);
+    CUDA_OK(launchRoot(in, in->partials[buffer], in->dWeights + (size_t)wIdx * in->C, in->dFreqs + (size_t)fIdx * in->Sp,
+                       cum == BEAGLE_OP_NONE ? nullptr : in->dScale + (size_t)cum * in->Ppad, pBegin, pEnd, dOutSlot));
+    return BEAGLE_SUCCESS;
+}
+
+int beagleCalculateRootLogLikelihoods(int instance, const int* bufferIndices, const int* categoryWeightsIndices,
+                                      const int* stateFrequenciesIndices, const int* cumulativeScaleIndices,
+                                      int count, double* outSumLogLikelihood) {
+    GET_INSTANCE(in, instance);
+    if (count != 1) return BEAGLE_ERROR_NO_IMPLEMENTATION;   // BEAST always passes 1 (BDLD:934-935)
+    int rc = rootLaunch(in, bufferIndices[0], categoryWeightsIndices[0], stateFrequenciesIndices[0],
+                        cumulativeScaleIndices[0], 0, in->P, in->dOut);
+    if (rc != BEAGLE_SUCCESS) return rc;
+    CUDA_OK(cudaMemcpyAsync(in->hOut, in->dOut, sizeof(double), cudaMemcpyDeviceToHost, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    *outSumLogLikelihood = in->hOut[0];
+    return std::isnan(in->hOut[0]) ? BEAGLE_ERROR_FLOATING_POINT : BEAGLE_SUCCESS;
+}
+
+int beagleCalculateRootLogLikelihoodsByPartition(int instance, const int* bufferIndices,
+                                                 const int* categoryWeightsIndices,
+                                                 const int* stateFrequenciesIndices,
+                                                 const int* cumulativeScaleIndices, const int* partitionIndices,
+                                                 int partitionCount, int count,
+                                                 double* outSumLogLikelihoodByPartition, double* outSumLogLikelihood) {
+    GET_INSTANCE(in, instance);
+    if (count != 1) return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    if (partitionCount < 1 || partitionCount > 1000) return BEAGLE_ERROR_OUT_OF_RANGE;
+    for (int k = 0; k < partitionCount; ++k) {
+        int part = partitionIndices[k];
+        if (!validRange(part, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        int rc = rootLaunch(in, bufferIndices[k], categoryWeightsIndices[k], stateFrequenciesIndices[k],
+                            cumulativeScaleIndices[k], in->partBegin[part], in->partEnd[part], in->dOut + k);
+        if (rc != BEAGLE_SUCCESS) return rc;
+    }
+    CUDA_OK(cudaMemcpyAsync(in->hOut, in->dOut, sizeof(double) * partitionCount, cudaMemcpyDeviceToHost, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    double total = 0.0;
+    for (int k = 0; k < partitionCount; ++k) { outSumLogLikelihoodByPartition[k] = in->hOut[k]; total += in->hOut[k]; }
+    *outSumLogLikelihood = total;
+    return std::isnan(total) ? BEAGLE_ERROR_FLOATING_POINT : BEAGLE_SUCCESS;
+}
+
+int beagleGetSiteLogLikelihoods(int instance, double* outLogLikelihoods) {
+    GET_INSTANCE(in, instance);
+    CUDA_OK(cudaMemcpyAsync(outLogLikelihoods, in->dSite, sizeof(double) * in->P, cudaMemcpyDeviceToHost, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+// ---- engine extensions ------------------------------------------------------------------------
+int b200SetKernelTiming(int instance, int enable) {
+    GET_INSTANCE(in, instance);
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    for (int c = 0; c < T_CLASSES; ++c) {
+        for (auto& ev : in->timed[c]) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+        in->timed[c].clear();
+        in->timedMs[c] = 0.0;
+        in->timedLaunches[c] = 0;
+    }
+    in->timing = enable != 0;
+    return BEAGLE_SUCCESS;
+}
+
+int b200GetKernelTiming(int instance, int which, double* outMilliseconds, long* outLaunches) {
+    GET_INSTANCE(in, instance);
+    if (which < 0 || which >= T_CLASSES) return BEAGLE_ERROR_OUT_OF_RANGE;
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    for (auto& ev : in->timed[which]) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) in->timedMs[which] += ms;
+        in->timedLaunches[which]++;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    in->timed[which].clear();
+    if (outMilliseconds) *outMilliseconds = in->timedMs[which];
+    if (outLaunches) *outLaunches = in->timedLaunches[which];
+    return BEAGLE_SUCCESS;
+}
+
+void* b200HostAlloc(long bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void b200HostFree(void* p) { if (p) cudaFreeHost(p); }
+
+int b200RootLogLikelihoodDevice(int instance, int bufferIndex, int categoryWeightsIndex, int stateFrequenciesIndex,
+                                int cumulativeScaleIndex, void** outDevicePointer, void** outStream) {
+    GET_INSTANCE(in, instance);
+    int rc = rootLaunch(in, bufferIndex, categoryWeightsIndex, stateFrequenciesIndex, cumulativeScaleIndex, 0, in->P,
+                        in->dOut);
+    if (rc != BEAGLE_SUCCESS) return rc;
+    if (outDevicePointer) *outDevicePointer = in->dOut;
+    if (outStream) *outStream = in->stream;
+    return BEAGLE_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// engine.h -- internal types of the B200 tree-likelihood engine (not part of the ABI).
+//
+// One Instance owns every device allocation between beagleCreateInstance and
+// beagleFinalizeInstance.  Device layout (DESIGN.md "Data layout in HBM"):
+//   partials buffer   [C][Ppad][Sp] f64   (Ppad = P rounded up to 32 patterns, Sp = padded states)
+//   compact tip       [Ppad] u8 + [Ppad] i32, value S = gap/unknown
+//   transition matrix [C][Sp(child j)][Sp(parent i)] f64  -- stored TRANSPOSED so that a compact-tip
+//                     child reads one contiguous column and lanes indexed by parent state are coalesced
+//   scale buffer      [Ppad] f64 (raw factors, or logs under SCALERS_LOG; cumulative buffers: logs)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <mutex>
+#include <vector>
+
+namespace b200 {
+
+struct alignas(16) DevOp {
+    double* dest;
+    const double* c1;      // child-1 partials, or nullptr when the child is a compact tip
+    const double* c2;
+    const void* s1;        // child-1 compact states (u8 for the 4-state path, i32 otherwise)
+    const void* s2;
+    const double* m1;      // transposed matrices of the two branches
+    const double* m2;
+    double* scaleWrite;    // nullptr = BEAGLE_OP_NONE
+    const double* scaleRead;
+    double* cumScale;
+    int pBegin, pEnd;      // pattern range the op applies to (a partition, or [0,P))
+    int srcSlot1, srcSlot2;  // operand-stack slots (4-state stack walk); -1 = read from global
+    int dstSlot;             // operand-stack slot the result is parked in; -1 = none
+    int pad_;
+};
+
+enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
+
+struct Instance {
+    int id = -1, device = 0, resource = 0;
+    int tipCount = 0, nPartials = 0, nCompact = 0, S = 0, P = 0, nEigen = 0, nMatrices = 0, C = 0, nScale = 0;
+    int Sp = 0, Ppad = 0, nBuffers = 0, nSets = 1;
+    long flags = 0;
+    bool logScalers = false, complexEigen = false;
+    cudaStream_t stream = nullptr;
+    int smCount = 148;
+    size_t maxSmemOptin = 0;
+
+    size_t partialsElems = 0;                 // C*Ppad*Sp
+    std::vector<double*> partials;            // lazily allocated, one per buffer index
+    std::vector<uint8_t*> states8;
+    std::vector<int*> states32;
+    std::vector<void*> slabs;                 // backing allocations handed out by the bump allocator
+    char* slabCur = nullptr;
+    size_t slabLeft = 0;
+
+    double* dEigen = nullptr;                 // [nEigen][2*S*S + 2*S]
+    double* dMat = nullptr;                   // [nMatrices][C][Sp][Sp] transposed
+    double* dRates = nullptr;                 // [nSets][C]
+    double* dWeights = nullptr;               // [nSets][C]
+    double* dFreqs = nullptr;                 // [nSets][Sp]
+    double* dScale = nullptr;                 // [nScale][Ppad]
+    double* dPatternWeights = nullptr;        // [Ppad], zero padded
+    int* dPatternPartitions = nullptr;        // [Ppad]
+    double* dSite = nullptr;                  // [Ppad]
+    double* dBlockSums = nullptr;
+    double* dOut = nullptr;                   // [maxPartitions + 1]
+    unsigned int* dCounter = nullptr;
+    int partitionCount = 1;
+    std::vector<int> partBegin, partEnd;      // contiguous pattern ranges per partition
+    std::vector<int> hostPartitions;
+
+    // pinned staging ring for the small per-call arrays (ops, indices, branch lengths)
+    char* hStage = nullptr;
+    char* dStage = nullptr;
+    size_t stageSize = 0, stagePos = 0;
+    double* hOut = nullptr;                   // pinned result landing zone
+
+    // kernel timing (bench.py roofline): events around every launch of a class
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[T_CLASSES];
+    double timedMs[T_CLASSES] = {0, 0, 0};
+    long timedLaunches[T_CLASSES] = {0, 0, 0};
+
+    // tuning knobs (environment overridable, see api.cu)
+    int walkBlock = 64;
+    int walkVariant = 0;
+    int reorder = 1;
+};
+
+// ---- kernel launchers (kernels.cu) -----------------------------------------------------------
+cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const int* dEigenIdx,
+                                     const int* dRateSet, const double* dLengths, int count);
+cudaError_t launchWalk4(Instance* in, const DevOp* dOps, int nOps, int stackDepth);
+cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, int nOps);
+cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
+                       const double* cumScale, int pBegin, int pEnd, double* dOutSlot);
+cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,
+                                  int pBegin, int pEnd);
+cudaError_t launchRescalePartialsForGet(Instance* in, double* tmp, const double* cum);
+
+}  // namespace b200

@@ -1,0 +1,480 @@
+// kernels.cu -- hand-written sm_100a kernels of the tree-likelihood hot path.
+//
+//   k_transition   : P_c(t) = Evec diag(exp(Eval r_c t)) Ievc           (updateTransitionMatrices)
+//   k_walk4        : 4-state (nucleotide) partials, WARP-OWNED PATTERN COLUMNS walking the whole
+//                    operation list on-device; per-thread shared-memory operand stack (updatePartials)
+//   k_walk_generic : any state count, BLOCK-OWNED pattern tiles walking the list  (updatePartials)
+//   k_root         : frequency/category integration + log + scalers + weighted reduction
+//   k_scale_accum  : cumulative scale buffers
+//
+// Why "walk": Felsenstein pruning has no cross-pattern data flow.  A pattern column (all categories
+// and states of one site pattern) of a parent depends only on the same column of its children, so a
+// warp (or block) that owns a set of columns can execute the ENTIRE post-order operation list for
+// them without any grid-wide synchronisation: one launch per updatePartials call instead of one per
+// node, and children produced earlier in the same list are read back from shared memory (the
+// operand stack), not from HBM.  The only mandatory HBM traffic is the write of every destination
+// buffer (BEAST needs them for later incremental updates) plus tips and pre-existing siblings.
+#include "engine.h"
+
+#include <cfloat>
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+}
+// read-only path for data produced by an EARLIER launch (matrices)
+__device__ __forceinline__ void ldg256_nc(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(double* p, const double (&v)[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// transition matrices
+// ---------------------------------------------------------------------------------------------
+// grid (count, C); dynamic smem: ec[S], ss[S], pt[S](int).  Follows BaseSubstitutionModel.java:206-241
+// (real) / ComplexColtEigenSystem.java:71-139 (2x2 blocks), abs() convention; output TRANSPOSED.
+__global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenStride, int S, int Sp, int C,
+                             int complexForm, const double* __restrict__ ratesBase,
+                             const int* __restrict__ probIdx, const int* __restrict__ eigenIdx,
+                             const int* __restrict__ rateSet, const double* __restrict__ lengths,
+                             double* __restrict__ matBase) {
+    extern __shared__ double sm[];
+    double* ec = sm;
+    double* ss = sm + S;
+    int* pt = reinterpret_cast<int*>(sm + 2 * S);
+    const int b = blockIdx.x, c = blockIdx.y;
+    const double* E = eigenBase + (size_t)eigenIdx[b] * eigenStride;
+    const double* evec = E;
+    const double* ievc = E + (size_t)S * S;
+    const double* eval = E + 2 * (size_t)S * S;
+    const double d = lengths[b] * ratesBase[(size_t)rateSet[b] * C + c];
+    for (int k = threadIdx.x; k < S; k += blockDim.x) {
+        double im = complexForm ? eval[S + k] : 0.0;
+        if (im == 0.0) {
+            ec[k] = exp(d * eval[k]); ss[k] = 0.0; pt[k] = k;
+        } else {
+            // rows of a conjugate pair are adjacent; the FIRST row's imaginary part drives the block
+            // robust pairing: count consecutive non-zero imaginary rows above k
+            int run = 0;
+            for (int q = k - 1; q >= 0 && eval[S + q] != 0.0; --q) ++run;
+            const bool first = (run % 2 == 0);
+            int k0 = first ? k : k - 1;
+            double bb = eval[S + k0];
+            double expat = exp(d * eval[k0]);
+            ec[k] = expat * cos(d * bb);
+            ss[k] = (first ? 1.0 : -1.0) * expat * sin(d * bb);
+            pt[k] = first ? k + 1 : k - 1;
+        }
+    }
+    __syncthreads();
+    double* out = matBase + ((size_t)probIdx[b] * C + c) * Sp * Sp;
+    for (int idx = threadIdx.x; idx < Sp * Sp; idx += blockDim.x) {
+        int j = idx / Sp, i = idx % Sp;          // out[j][i] = P[i][j]
+        double acc = 0.0;
+        if (i < S && j < S) {
+            for (int k = 0; k < S; ++k) {
+                double iexp = ec[k] * ievc[(size_t)k * S + j] + ss[k] * ievc[(size_t)pt[k] * S + j];
+                acc += evec[(size_t)i * S + k] * iexp;
+            }
+            acc = fabs(acc);
+        }
+        out[idx] = acc;
+    }
+}
+
+cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const int* dEigenIdx,
+                                     const int* dRateSet, const double* dLengths, int count) {
+    if (count <= 0) return cudaSuccess;
+    size_t smem = (size_t)in->S * (2 * sizeof(double) + sizeof(int)) + 16;
+    int threads = in->Sp * in->Sp >= 1024 ? 256 : (in->Sp * in->Sp >= 128 ? 128 : 32);
+    dim3 grid(count, in->C);
+    k_transition<<<grid, threads, smem, in->stream>>>(in->dEigen, 2 * (size_t)in->S * in->S + 2 * in->S, in->S,
+                                                      in->Sp, in->C, in->complexEigen ? 1 : 0, in->dRates,
+                                                      dProbIdx, dEigenIdx, dRateSet, dLengths, in->dMat);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4-state walk
+// ---------------------------------------------------------------------------------------------
+// Warp layout: CP categories (power of two >= C) x G = 32/CP consecutive patterns.  lane = c*G + g.
+// Each thread owns the 4 states of one (pattern, category) cell = 32 contiguous bytes in [C][Ppad][4].
+// STACK: per-thread operand stack in shared memory, slot s of thread t split into two 16-byte halves
+//        laid out [slot][half][thread] so that every LDS.128/STS.128 is bank-conflict free.
+template <int CP, bool STACK>
+__global__ void __launch_bounds__(256)
+k_walk4(const DevOp* __restrict__ ops, int nOps, int S, int C, int Ppad, int logScalers) {
+    constexpr int G = 32 / CP;
+    extern __shared__ double2 stackMem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int c = lane / G;
+    const int p = warp * G + (lane % G);
+    const bool cellValid = (c < C) && (p < Ppad);
+    const size_t off = ((size_t)(cellValid ? c : 0) * Ppad + (cellValid ? p : 0)) * 4;
+    const size_t moff = (size_t)(cellValid ? c : 0) * 16;
+    const int nthreads = blockDim.x;
+
+    for (int k = 0; k < nOps; ++k) {
+        // the op record is warp-uniform: fetched through the read-only path, broadcast by L1
+        const DevOp* op = ops + k;
+        const double* c1 = op->c1;
+        const double* c2 = op->c2;
+        const int4 rng = *reinterpret_cast<const int4*>(&op->pBegin);   // pBegin,pEnd,srcSlot1,srcSlot2
+        const int dstSlot = op->dstSlot;
+        const bool active = cellValid && p >= rng.x && p < rng.y;
+
+        double a[4], b[4], d[4];
+        // ---- child 1 ------------------------------------------------------------------------
+        {
+            const double* m = op->m1 + moff;
+            if (STACK && rng.z >= 0) {
+                double2 lo = stackMem[(rng.z * 2 + 0) * nthreads + threadIdx.x];
+                double2 hi = stackMem[(rng.z * 2 + 1) * nthreads + threadIdx.x];
+                double x[4] = {lo.x, lo.y, hi.x, hi.y};
+                double r0[4], r1[4], r2[4], r3[4];
+                ldg256_nc(m, r0); ldg256_nc(m + 4, r1); ldg256_nc(m + 8, r2); ldg256_nc(m + 12, r3);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = r0[i] * x[0] + r1[i] * x[1] + r2[i] * x[2] + r3[i] * x[3];
+            } else if (c1 != nullptr) {
+                double x[4];
+                if (active) ldg256(c1 + off, x); else { x[0] = x[1] = x[2] = x[3] = 0.0; }
+                double r0[4], r1[4], r2[4], r3[4];
+                ldg256_nc(m, r0); ldg256_nc(m + 4, r1); ldg256_nc(m + 8, r2); ldg256_nc(m + 12, r3);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = r0[i] * x[0] + r1[i] * x[1] + r2[i] * x[2] + r3[i] * x[3];
+            } else {
+                const uint8_t* st = static_cast<const uint8_t*>(op->s1);
+                int s = active ? (int)__ldg(st + p) : S;
+                if (s < S) { ldg256_nc(m + 4 * s, a); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = (i < S) ? 1.0 : 0.0;
+                }
+            }
+        }
+        // ---- child 2 ------------------------------------------------------------------------
+        {
+            const double* m = op->m2 + moff;
+            if (STACK && rng.w >= 0) {
+                double2 lo = stackMem[(rng.w * 2 + 0) * nthreads + threadIdx.x];
+                double2 hi = stackMem[(rng.w * 2 + 1) * nthreads + threadIdx.x];
+                double x[4] = {lo.x, lo.y, hi.x, hi.y};
+                double r0[4], r1[4], r2[4], r3[4];
+                ldg256_nc(m, r0); ldg256_nc(m + 4, r1); ldg256_nc(m + 8, r2); ldg256_nc(m + 12, r3);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b[i] = r0[i] * x[0] + r1[i] * x[1] + r2[i] * x[2] + r3[i] * x[3];
+            } else if (c2 != nullptr) {
+                double x[4];
+                if (active) ldg256(c2 + off, x); else { x[0] = x[1] = x[2] = x[3] = 0.0; }
+                double r0[4], r1[4], r2[4], r3[4];
+                ldg256_nc(m, r0); ldg256_nc(m + 4, r1); ldg256_nc(m + 8, r2); ldg256_nc(m + 12, r3);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b[i] = r0[i] * x[0] + r1[i] * x[1] + r2[i] * x[2] + r3[i] * x[3];
+            } else {
+                const uint8_t* st = static_cast<const uint8_t*>(op->s2);
+                int s = active ? (int)__ldg(st + p) : S;
+                if (s < S) { ldg256_nc(m + 4 * s, b); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) b[i] = (i < S) ? 1.0 : 0.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = a[i] * b[i];
+
+        // ---- rescaling (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE) ---------
+        double* sw = op->scaleWrite;
+        const double* sr = op->scaleRead;
+        if (sw != nullptr) {
+            double m = active ? fmax(fmax(d[0], d[1]), fmax(d[2], d[3])) : 0.0;
+#pragma unroll
+            for (int sh = G; sh < 32; sh <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, sh));
+            if (m == 0.0) m = 1.0;
+            const double inv = 1.0 / m;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] *= inv;
+            if (active && c == 0) {
+                const double lm = log(m);
+                sw[p] = logScalers ? lm : m;
+                double* cum = op->cumScale;
+                if (cum != nullptr) cum[p] += lm;
+            }
+            __syncwarp();
+        } else if (sr != nullptr) {
+            double f = active ? sr[p] : 1.0;
+            if (logScalers) f = exp(f);
+            const double inv = 1.0 / f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] *= inv;
+        }
+
+        if (active) stg256(op->dest + off, d);
+        if (STACK && dstSlot >= 0) {
+            stackMem[(dstSlot * 2 + 0) * nthreads + threadIdx.x] = make_double2(d[0], d[1]);
+            stackMem[(dstSlot * 2 + 1) * nthreads + threadIdx.x] = make_double2(d[2], d[3]);
+        }
+    }
+}
+
+template <int CP>
+static cudaError_t launchWalk4T(Instance* in, const DevOp* dOps, int nOps, int stackDepth) {
+    constexpr int G = 32 / CP;
+    const int warps = (in->Ppad + G - 1) / G;
+    const int wpb = in->walkBlock / 32;
+    const int blocks = (warps + wpb - 1) / wpb;
+    const int log = in->logScalers ? 1 : 0;
+    if (stackDepth > 0) {
+        size_t smem = (size_t)stackDepth * 32 * in->walkBlock;
+        static bool attrSet[4] = {false, false, false, false};
+        (void)attrSet;
+        cudaFuncSetAttribute(k_walk4<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_walk4<CP, true><<<blocks, in->walkBlock, smem, in->stream>>>(dOps, nOps, in->S, in->C, in->Ppad, log);
+    } else {
+        k_walk4<CP, false><<<blocks, in->walkBlock, 0, in->stream>>>(dOps, nOps, in->S, in->C, in->Ppad, log);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launchWalk4(Instance* in, const DevOp* dOps, int nOps, int stackDepth) {
+    if (nOps <= 0) return cudaSuccess;
+    const int C = in->C;
+    if (C <= 1) return launchWalk4T<1>(in, dOps, nOps, stackDepth);
+    if (C <= 2) return launchWalk4T<2>(in, dOps, nOps, stackDepth);
+    if (C <= 4) return launchWalk4T<4>(in, dOps, nOps, stackDepth);
+    if (C <= 8) return launchWalk4T<8>(in, dOps, nOps, stackDepth);
+    if (C <= 16) return launchWalk4T<16>(in, dOps, nOps, stackDepth);
+    return launchWalk4T<32>(in, dOps, nOps, stackDepth);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic-state block walk
+// ---------------------------------------------------------------------------------------------
+// Block owns TP consecutive patterns and walks the op list; per (op, category) it stages the two
+// transposed matrices and the two child tiles in shared memory, computes the TP x Sp destination
+// tile (thread index = pattern-major, parent state fastest: conflict-free matrix reads, broadcast
+// child reads, coalesced stores), tracks per-pattern maxima for the optional rescale.
+__global__ void __launch_bounds__(256)
+k_walk_generic(const DevOp* __restrict__ ops, int nOps, int S, int Sp, int C, int Ppad, int TP,
+               int logScalers, int stageMatrices) {
+    extern __shared__ double smg[];
+    const size_t msz = stageMatrices ? (size_t)Sp * Sp : 0;
+    double* mt1s = smg;
+    double* mt2s = smg + msz;
+    double* x1 = smg + 2 * msz;
+    double* x2 = x1 + (size_t)TP * Sp;
+    unsigned long long* pmax = reinterpret_cast<unsigned long long*>(x2 + (size_t)TP * Sp);
+    const int p0 = blockIdx.x * TP;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tileElems = TP * Sp;
+
+    for (int k = 0; k < nOps; ++k) {
+        const DevOp op = ops[k];
+        const bool doMax = op.scaleWrite != nullptr;
+        if (doMax) for (int q = tid; q < TP; q += nt) pmax[q] = 0ull;
+        for (int c = 0; c < C; ++c) {
+            __syncthreads();
+            const double* m1g = op.m1 + (size_t)c * Sp * Sp;
+            const double* m2g = op.m2 + (size_t)c * Sp * Sp;
+            if (stageMatrices) {
+                for (int q = tid; q < Sp * Sp; q += nt) { mt1s[q] = m1g[q]; mt2s[q] = m2g[q]; }
+            }
+            const size_t tileOff = ((size_t)c * Ppad + p0) * Sp;
+            if (op.c1) for (int q = tid; q < tileElems; q += nt) x1[q] = op.c1[tileOff + q];
+            if (op.c2) for (int q = tid; q < tileElems; q += nt) x2[q] = op.c2[tileOff + q];
+            __syncthreads();
+            const double* mt1 = stageMatrices ? mt1s : m1g;
+            const double* mt2 = stageMatrices ? mt2s : m2g;
+            for (int q = tid; q < tileElems; q += nt) {
+                const int pl = q / Sp, i = q - pl * Sp;
+                const int p = p0 + pl;
+                const bool active = p >= op.pBegin && p < op.pEnd;
+                if (!active) continue;
+                double a, b;
+                if (op.c1) {
+                    a = 0.0;
+                    const double* xr = x1 + (size_t)pl * Sp;
+                    for (int j = 0; j < S; ++j) a += mt1[(size_t)j * Sp + i] * xr[j];
+                } else {
+                    int s = static_cast<const int*>(op.s1)[p];
+                    a = (s < S) ? mt1[(size_t)s * Sp + i] : ((i < S) ? 1.0 : 0.0);
+                }
+                if (op.c2) {
+                    b = 0.0;
+                    const double* xr = x2 + (size_t)pl * Sp;
+                    for (int j = 0; j < S; ++j) b += mt2[(size_t)j * Sp + i] * xr[j];
+                } else {
+                    int s = static_cast<const int*>(op.s2)[p];
+                    b = (s < S) ? mt2[(size_t)s * Sp + i] : ((i < S) ? 1.0 : 0.0);
+                }
+                const double d = a * b;
+                op.dest[tileOff + q] = d;
+                if (doMax) atomicMax(&pmax[pl], (unsigned long long)__double_as_longlong(d));
+            }
+        }
+        if (op.scaleWrite != nullptr || op.scaleRead != nullptr) {
+            __syncthreads();
+            for (int c = 0; c < C; ++c) {
+                const size_t tileOff = ((size_t)c * Ppad + p0) * Sp;
+                for (int q = tid; q < tileElems; q += nt) {
+                    const int pl = q / Sp;
+                    const int p = p0 + pl;
+                    if (p < op.pBegin || p >= op.pEnd) continue;
+                    double f;
+                    if (op.scaleWrite) {
+                        f = __longlong_as_double((long long)pmax[pl]);
+                        if (f == 0.0) f = 1.0;
+                    } else {
+                        f = op.scaleRead[p];
+                        if (logScalers) f = exp(f);
+                    }
+                    op.dest[tileOff + q] *= (1.0 / f);
+                }
+            }
+            if (op.scaleWrite) {
+                for (int pl = tid; pl < TP; pl += nt) {
+                    const int p = p0 + pl;
+                    if (p < op.pBegin || p >= op.pEnd) continue;
+                    double m = __longlong_as_double((long long)pmax[pl]);
+                    if (m == 0.0) m = 1.0;
+                    const double lm = log(m);
+                    op.scaleWrite[p] = logScalers ? lm : m;
+                    if (op.cumScale) op.cumScale[p] += lm;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, int nOps) {
+    if (nOps <= 0) return cudaSuccess;
+    const int Sp = in->Sp;
+    const size_t budget = in->maxSmemOptin > 16384 ? in->maxSmemOptin - 2048 : 46000;
+    int stage = (2 * (size_t)Sp * Sp * 8 + 2 * 8 * (size_t)Sp * 8 + 64 <= budget) ? 1 : 0;
+    size_t fixed = stage ? 2 * (size_t)Sp * Sp * 8 : 0;
+    int TP = 32;
+    while (TP > 1 && fixed + (size_t)TP * (2 * Sp + 1) * 8 > budget) TP >>= 1;
+    while (TP > 8 && (in->Ppad + TP - 1) / TP < in->smCount) TP >>= 1;   // keep every SM busy
+    size_t smem = fixed + (size_t)TP * (2 * Sp + 1) * 8;
+    cudaFuncSetAttribute(k_walk_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int blocks = (in->Ppad + TP - 1) / TP;
+    k_walk_generic<<<blocks, 256, smem, in->stream>>>(dOps, nOps, in->S, Sp, in->C, in->Ppad, TP,
+                                                      in->logScalers ? 1 : 0, stage);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// root integration + reduction
+// ---------------------------------------------------------------------------------------------
+// site[p] = log(sum_i pi_i (sum_c w_c root[c,p,i])) + cum[p]   (GeneralLikelihoodCore.java:358-408)
+// out     = sum_p weight[p] site[p], deterministic two-level tree (fixed shape => reproducible).
+__global__ void __launch_bounds__(256)
+k_root(const double* __restrict__ root, const double* __restrict__ weights, const double* __restrict__ freqs,
+       const double* __restrict__ cumScale, const double* __restrict__ patternWeights, int S, int Sp, int C,
+       int Ppad, int pBegin, int pEnd, double* __restrict__ site, double* __restrict__ blockSums,
+       unsigned int* __restrict__ counter, double* __restrict__ out) {
+    __shared__ double red[256];
+    __shared__ bool last;
+    const int p = pBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    double contrib = 0.0;
+    if (p < pEnd) {
+        double sum = 0.0;
+        for (int i = 0; i < S; ++i) {
+            double integ = 0.0;
+            for (int c = 0; c < C; ++c) integ += root[((size_t)c * Ppad + p) * Sp + i] * weights[c];
+            sum += freqs[i] * integ;
+        }
+        double s = log(sum);
+        if (cumScale != nullptr) s += cumScale[p];
+        site[p] = s;
+        contrib = patternWeights[p] * s;
+    }
+    red[threadIdx.x] = contrib;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        blockSums[blockIdx.x] = red[0];
+        __threadfence();
+        unsigned int done = atomicAdd(counter, 1u);
+        last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double acc = 0.0;
+        for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) acc += blockSums[q];
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int w = 128; w > 0; w >>= 1) {
+            if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { *out = red[0]; *counter = 0u; }
+    }
+}
+
+cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
+                       const double* cumScale, int pBegin, int pEnd, double* dOutSlot) {
+    int n = pEnd - pBegin;
+    if (n <= 0) return cudaMemsetAsync(dOutSlot, 0, sizeof(double), in->stream);
+    int blocks = (n + 255) / 256;
+    k_root<<<blocks, 256, 0, in->stream>>>(root, weights, freqs, cumScale, in->dPatternWeights, in->S, in->Sp,
+                                           in->C, in->Ppad, pBegin, pEnd, in->dSite, in->dBlockSums,
+                                           in->dCounter, dOutSlot);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// scale-factor accumulation:  cum[p] += sign * sum_k log-factor_k[p]   (BDLD:915-926)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_scale_accum(const double* __restrict__ scaleBase, int Ppad, const int* __restrict__ idx,
+                              int count, double* __restrict__ cum, double sign, int logScalers, int pBegin,
+                              int pEnd) {
+    const int p = pBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pEnd) return;
+    double acc = 0.0;
+    for (int k = 0; k < count; ++k) {
+        double f = scaleBase[(size_t)idx[k] * Ppad + p];
+        acc += logScalers ? f : log(f);
+    }
+    cum[p] += sign * acc;
+}
+
+cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,
+                                  int pBegin, int pEnd) {
+    int n = pEnd - pBegin;
+    if (n <= 0 || count <= 0) return cudaSuccess;
+    k_scale_accum<<<(n + 127) / 128, 128, 0, in->stream>>>(in->dScale, in->Ppad, dIdx, count, cum, sign,
+                                                           in->logScalers ? 1 : 0, pBegin, pEnd);
+    return cudaGetLastError();
+}
+
+// getPartials with a cumulative scale index: tmp[c,p,i] *= exp(cum[p])
+__global__ void k_unscale(double* __restrict__ tmp, const double* __restrict__ cum, int Sp, int Ppad, size_t n) {
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int p = (int)((q / Sp) % Ppad);
+    tmp[q] *= exp(cum[p]);
+}
+
+cudaError_t launchRescalePartialsForGet(Instance* in, double* tmp, const double* cum) {
+    size_t n = in->partialsElems;
+    k_unscale<<<(unsigned)((n + 255) / 256), 256, 0, in->stream>>>(tmp, cum, in->Sp, in->Ppad, n);
+    return cudaGetLastError();
+}
+
+}  // namespace b200
