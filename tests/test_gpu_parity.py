@@ -80,7 +80,10 @@ def test_oracle_parity(tips, patterns, cats, states, scheme):
     # per-pattern values and every internal node's partials agree too
     assert np.allclose(g.getSiteLogLikelihoods(), o.getSiteLogLikelihoods(), rtol=1e-10, atol=1e-12)
     for node in range(tree.tipCount, tree.nodeCount):
-        assert np.allclose(g.getPartials(node), o.getPartials(node), rtol=1e-9, atol=1e-300), node
+        pg, po = g.getPartials(node), o.getPartials(node)
+        # relative agreement, with an absolute floor for entries that are pure cancellation residue
+        # of P(t) at tiny rate*time (|P_ij| ~ 1e-13): exp() ulp differences dominate there
+        assert np.allclose(pg, po, rtol=1e-9, atol=1e-13 * po.max()), node
     g.finalize()
 
 
@@ -106,7 +109,7 @@ def test_scalers_raw_and_log(log_scalers):
 def test_underflow_protocol_deep_tree():
     """Deep tree: unscaled evaluation underflows -> -Inf -> BEAST switches scaling on and retries
     (BDLD:946-996).  The re-enactment must converge to the oracle's scaled value."""
-    tree, pats, model, site = H.synthetic_case(700, 48, 4, seed=9, rootHeight=60.0)
+    tree, pats, model, site = H.synthetic_case(700, 48, 4, seed=9, rootHeight=3000.0)
     g, o = _pair(tree, pats, model, site, rescalingScheme=S_.DYNAMIC, delayRescalingUntilUnderflow=True)
     tg, to = tdl.TreeDataLikelihood(g, tree), tdl.TreeDataLikelihood(o, tree)
     lg, lo = tg.getLogLikelihood(), to.getLogLikelihood()

@@ -60,3 +60,35 @@ def test_jc69_eigenvalues_match_beagle_tiny_constants():
     _, _, model, _, _ = H.tiny_case()
     lam = np.sort(model.getEigenDecomposition().Eval)
     assert np.allclose(lam, [-4 / 3, -4 / 3, -4 / 3, 0.0], atol=1e-14)
+
+
+# ---- the C restatement (oracle/beagle_cpu.c: checker + cpu_baseline) is pinned the same way ------
+@pytest.fixture(scope="module")
+def cport():
+    from beast_mcmc_b200 import build
+    build.build_oracle()
+    from oracle import cpu
+    return cpu
+
+
+@pytest.mark.parametrize("name", list(H.primate_cases().keys()))
+def test_c_port_primates_golden(cport, name):
+    model, site, expected = H.primate_cases()[name]
+    d = tdl.BeagleDataLikelihoodDelegate(H.primate_tree(), H.primate_patterns(), model, site, cport.factory(threads=3),
+                                         delayRescalingUntilUnderflow=False)
+    assert _fmt(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood()) == _fmt(expected)
+    d.finalize()
+
+
+@pytest.mark.parametrize("states,cats,scheme", [(4, 4, "none"), (4, 5, "always"), (20, 2, "always"), (61, 1, "none")])
+def test_c_port_matches_numpy_oracle(cport, states, cats, scheme):
+    tree, pats, model, site = H.synthetic_case(24, 150, cats, seed=states + cats, stateCount=states)
+    vals = []
+    for f in (cport.factory(threads=4), H.oracle_factory()):
+        d = tdl.BeagleDataLikelihoodDelegate(tree, pats, model, site, f, rescalingScheme=scheme,
+                                             delayRescalingUntilUnderflow=False)
+        vals.append(tdl.TreeDataLikelihood(d, tree).getLogLikelihood())
+        sites = d.getSiteLogLikelihoods()
+        vals.append(sites)
+    assert abs(vals[0] - vals[2]) <= 1e-12 * abs(vals[2])
+    assert np.allclose(vals[1], vals[3], rtol=1e-12, atol=1e-13)
