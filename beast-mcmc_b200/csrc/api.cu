@@ -109,31 +109,14 @@ int uploadSmall(Instance* in, void* dDst, const void* src, size_t bytes) {
     return BEAGLE_SUCCESS;
 }
 
-// bump allocator over large slabs: per-buffer storage is handed out on first use
-void* slabAlloc(Instance* in, size_t bytes) {
-    bytes = (bytes + 255) & ~size_t(255);
-    if (bytes > in->slabLeft) {
-        size_t slab = std::max(bytes * 64, size_t(64) << 20);
-        slab = std::min(slab, std::max(bytes, size_t(2) << 30));
-        void* p = nullptr;
-        if (cudaMalloc(&p, slab) != cudaSuccess) {
-            cudaGetLastError();
-            slab = bytes;
-            if (cudaMalloc(&p, slab) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        }
-        in->slabs.push_back(p);
-        in->slabCur = static_cast<char*>(p);
-        in->slabLeft = slab;
-    }
-    void* r = in->slabCur;
-    in->slabCur += bytes;
-    in->slabLeft -= bytes;
-    return r;
-}
-
+// partials live in ONE contiguous slab (index addressing in the walk kernels); a buffer index gets
+// its slot on first use (tips that stay compact never consume one)
 double* ensurePartials(Instance* in, int idx) {
-    if (in->partials[idx] == nullptr)
-        in->partials[idx] = static_cast<double*>(slabAlloc(in, in->partialsElems * sizeof(double)));
+    if (in->partials[idx] == nullptr) {
+        if (in->nextSlot >= in->nSlots) return nullptr;
+        in->slotOf[idx] = in->nextSlot++;
+        in->partials[idx] = in->partialsBase + (size_t)in->slotOf[idx] * in->partialsElems;
+    }
     return in->partials[idx];
 }
 
@@ -142,7 +125,7 @@ bool validRange(int idx, int n) { return idx >= 0 && idx < n; }
 void destroyInstance(Instance* in) {
     cudaSetDevice(in->device);
     if (in->stream) cudaStreamSynchronize(in->stream);
-    for (void* p : in->slabs) cudaFree(p);
+    cudaFree(in->partialsBase); cudaFree(in->states8Base); cudaFree(in->states32Base);
     cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dRates); cudaFree(in->dWeights);
     cudaFree(in->dFreqs); cudaFree(in->dScale); cudaFree(in->dPatternWeights);
     cudaFree(in->dPatternPartitions); cudaFree(in->dSite); cudaFree(in->dBlockSums); cudaFree(in->dOut);
@@ -267,14 +250,14 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         if (in->partials[o.c1] == nullptr && in->states32[o.c1] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
         if (in->partials[o.c2] == nullptr && in->states32[o.c2] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
     }
-    const bool fourState = in->Sp == 4;
+    const bool fourState = in->matCP > 0;
     std::vector<int> order;
     planOrder(hops, in->nBuffers, in->reorder && !byPartition, order);
 
     // ---- stack slots (4-state path only): one backward pass finds, for every produced value, the
     // position of its LAST reader inside this list (before the buffer is re-written); the forward
     // pass then parks results in slots and frees each slot at that last read.
-    const int maxDepth = (fourState && !byPartition && in->walkVariant >= 1) ? envInt("B200_STACK_DEPTH", 12) : 0;
+    const int maxDepth = (fourState && !byPartition && in->walkVariant >= 1) ? in->stackDepthMax : 0;
     std::vector<int> lastReadOfProd(maxDepth > 0 ? n : 0, -1);
     if (maxDepth > 0) {
         std::vector<int> lastRead(in->nBuffers, -1);
@@ -290,26 +273,14 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     std::vector<int> freeSlots;
     int depthUsed = 0;
 
-    std::vector<DevOp> dops(n);
+    const bool fourPath = in->matCP > 0;
+    std::vector<DevOp> dops(fourPath ? 0 : n);
+    std::vector<Op4> ops4(fourPath ? n : 0);
     for (int pos = 0; pos < n; ++pos) {
         const HostOp& o = hops[order[pos]];
-        DevOp& d = dops[pos];
-        memset(&d, 0, sizeof d);
-        d.dest = in->partials[o.dest];
-        const bool t1 = in->states32[o.c1] != nullptr && in->partials[o.c1] == nullptr;
-        const bool t2 = in->states32[o.c2] != nullptr && in->partials[o.c2] == nullptr;
-        d.c1 = t1 ? nullptr : in->partials[o.c1];
-        d.c2 = t2 ? nullptr : in->partials[o.c2];
-        d.s1 = t1 ? (fourState ? (const void*)in->states8[o.c1] : (const void*)in->states32[o.c1]) : nullptr;
-        d.s2 = t2 ? (fourState ? (const void*)in->states8[o.c2] : (const void*)in->states32[o.c2]) : nullptr;
-        d.m1 = in->dMat + (size_t)o.m1 * in->C * in->Sp * in->Sp;
-        d.m2 = in->dMat + (size_t)o.m2 * in->C * in->Sp * in->Sp;
-        d.scaleWrite = o.sw >= 0 ? in->dScale + (size_t)o.sw * in->Ppad : nullptr;
-        d.scaleRead = o.sr >= 0 ? in->dScale + (size_t)o.sr * in->Ppad : nullptr;
-        d.cumScale = (o.cum >= 0 && o.sw >= 0) ? in->dScale + (size_t)o.cum * in->Ppad : nullptr;
-        if (byPartition) { d.pBegin = in->partBegin[o.part]; d.pEnd = in->partEnd[o.part]; }
-        else { d.pBegin = 0; d.pEnd = in->P; }
-        d.srcSlot1 = d.srcSlot2 = d.dstSlot = -1;
+        const bool t1 = in->states32[o.c1] != nullptr;
+        const bool t2 = in->states32[o.c2] != nullptr;
+        int srcSlot1 = -1, srcSlot2 = -1, dstSlot = -1;
         if (maxDepth > 0) {
             auto take = [&](int buf, bool isTip) -> int {
                 if (isTip) return -1;
@@ -317,40 +288,64 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
                 if (slot >= 0 && slotFreeAt[buf] == pos) { freeSlots.push_back(slot); slotOf[buf] = -1; }
                 return slot;
             };
-            d.srcSlot1 = take(o.c1, t1);
-            d.srcSlot2 = (o.c2 == o.c1) ? d.srcSlot1 : take(o.c2, t2);
+            srcSlot1 = take(o.c1, t1);
+            srcSlot2 = (o.c2 == o.c1) ? srcSlot1 : take(o.c2, t2);
             if (slotOf[o.dest] >= 0) { freeSlots.push_back(slotOf[o.dest]); slotOf[o.dest] = -1; }   // stale value
             if (lastReadOfProd[pos] > pos) {         // a later op of this list reads the result
                 int slot = -1;
                 if (!freeSlots.empty()) { slot = freeSlots.back(); freeSlots.pop_back(); }
                 else if (depthUsed < maxDepth) slot = depthUsed++;
-                if (slot >= 0) { slotOf[o.dest] = slot; slotFreeAt[o.dest] = lastReadOfProd[pos]; d.dstSlot = slot; }
+                if (slot >= 0) { slotOf[o.dest] = slot; slotFreeAt[o.dest] = lastReadOfProd[pos]; dstSlot = slot; }
             }
         }
-    }
-    void* dOps = stage(in, dops.data(), sizeof(DevOp) * n);
-    if (dOps == nullptr) {
-        // list larger than the ring: fall back to a one-off allocation
-        void* tmp = nullptr;
-        CUDA_OK(cudaMalloc(&tmp, sizeof(DevOp) * n));
-        CUDA_OK(cudaMemcpyAsync(tmp, dops.data(), sizeof(DevOp) * n, cudaMemcpyHostToDevice, in->stream));
-        CUDA_OK(cudaStreamSynchronize(in->stream));
-        cudaError_t e;
-        {
-            TimedScope ts(in, T_PARTIALS);
-            e = fourState ? launchWalk4(in, static_cast<DevOp*>(tmp), n, depthUsed)
-                          : launchWalkGeneric(in, static_cast<DevOp*>(tmp), n);
+        const int pBegin = byPartition ? in->partBegin[o.part] : 0;
+        const int pEnd = byPartition ? in->partEnd[o.part] : in->P;
+        const int cum = (o.cum >= 0 && o.sw >= 0) ? o.cum : -1;
+        if (fourPath) {
+            Op4& d = ops4[pos];
+            d.dest = in->slotOf[o.dest];
+            d.c1 = t1 ? -(o.c1 + 1) : in->slotOf[o.c1];
+            d.c2 = t2 ? -(o.c2 + 1) : in->slotOf[o.c2];
+            d.m1 = o.m1; d.m2 = o.m2; d.sw = o.sw; d.sr = o.sr; d.cum = cum;
+            d.pBegin = pBegin; d.pEnd = pEnd;
+            d.slots = (unsigned)(srcSlot1 & 0xFF) | ((unsigned)(srcSlot2 & 0xFF) << 8) | ((unsigned)(dstSlot & 0xFF) << 16);
+            d.pad_ = 0;
+        } else {
+            DevOp& d = dops[pos];
+            memset(&d, 0, sizeof d);
+            d.dest = in->partials[o.dest];
+            d.c1 = t1 ? nullptr : in->partials[o.c1];
+            d.c2 = t2 ? nullptr : in->partials[o.c2];
+            d.s1 = t1 ? (const void*)in->states32[o.c1] : nullptr;
+            d.s2 = t2 ? (const void*)in->states32[o.c2] : nullptr;
+            d.m1 = in->dMat + (size_t)o.m1 * in->matStride;
+            d.m2 = in->dMat + (size_t)o.m2 * in->matStride;
+            d.scaleWrite = o.sw >= 0 ? in->dScale + (size_t)o.sw * in->Ppad : nullptr;
+            d.scaleRead = o.sr >= 0 ? in->dScale + (size_t)o.sr * in->Ppad : nullptr;
+            d.cumScale = cum >= 0 ? in->dScale + (size_t)cum * in->Ppad : nullptr;
+            d.pBegin = pBegin; d.pEnd = pEnd;
+            d.srcSlot1 = d.srcSlot2 = d.dstSlot = -1;
         }
-        cudaStreamSynchronize(in->stream);
-        cudaFree(tmp);
-        CUDA_OK(e);
-        return BEAGLE_SUCCESS;
     }
+    const void* hostOps = fourPath ? (const void*)ops4.data() : (const void*)dops.data();
+    const size_t opBytes = (fourPath ? sizeof(Op4) : sizeof(DevOp)) * (size_t)n;
+    void* dOps = stage(in, hostOps, opBytes);
+    void* tmp = nullptr;
+    if (dOps == nullptr) {
+        // list larger than the staging ring: one-off allocation
+        CUDA_OK(cudaMalloc(&tmp, opBytes));
+        CUDA_OK(cudaMemcpyAsync(tmp, hostOps, opBytes, cudaMemcpyHostToDevice, in->stream));
+        CUDA_OK(cudaStreamSynchronize(in->stream));
+        dOps = tmp;
+    }
+    cudaError_t e;
     {
         TimedScope ts(in, T_PARTIALS);
-        CUDA_OK(fourState ? launchWalk4(in, static_cast<DevOp*>(dOps), n, depthUsed)
-                          : launchWalkGeneric(in, static_cast<DevOp*>(dOps), n));
+        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), n, depthUsed)
+                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), n);
     }
+    if (tmp != nullptr) { cudaStreamSynchronize(in->stream); cudaFree(tmp); }
+    CUDA_OK(e);
     return BEAGLE_SUCCESS;
 }
 
@@ -420,6 +415,16 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
         in->flags |= BEAGLE_FLAG_SCALING_DYNAMIC;
     }
     in->partialsElems = (size_t)in->C * in->Ppad * in->Sp;
+    if (in->Sp == 4 && in->C <= 32) {
+        int cp = 1;
+        while (cp < in->C) cp <<= 1;
+        in->matCP = cp;
+        in->matStride = (size_t)16 * cp;
+    } else {
+        in->matCP = 0;
+        in->matStride = (size_t)in->C * in->Sp * in->Sp;
+    }
+    in->slotOf.assign(in->nBuffers, -1);
     in->partials.assign(in->nBuffers, nullptr);
     in->states8.assign(in->nBuffers, nullptr);
     in->states32.assign(in->nBuffers, nullptr);
@@ -427,13 +432,14 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     if (in->walkBlock < 32 || in->walkBlock > 256 || (in->walkBlock & 31)) in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 1);
     in->reorder = envInt("B200_REORDER", 1);
+    in->stackDepthMax = std::min(64, std::max(0, envInt("B200_STACK_DEPTH", 12)));
 
     cudaDeviceProp prop;
     bool ok = cudaGetDeviceProperties(&prop, in->device) == cudaSuccess;
     if (ok) { in->smCount = prop.multiProcessorCount; in->maxSmemOptin = prop.sharedMemPerBlockOptin; }
     ok = ok && cudaStreamCreateWithFlags(&in->stream, cudaStreamNonBlocking) == cudaSuccess;
     const size_t eigenStride = 2 * (size_t)in->S * in->S + 2 * in->S;
-    const size_t matElems = (size_t)in->nMatrices * in->C * in->Sp * in->Sp;
+    const size_t matElems = (size_t)in->nMatrices * in->matStride;
     const int rootBlocks = (in->Ppad + 255) / 256;
     in->stageSize = size_t(8) << 20;
     auto alloc = [&](auto** p, size_t elems) {
@@ -456,6 +462,18 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     alloc(&in->dOut, 1024);
     alloc(&in->dCounter, 4);
     alloc(&in->dStage, in->stageSize);
+    alloc(&in->states8Base, (size_t)std::max(1, in->tipCount) * in->Ppad);
+    alloc(&in->states32Base, (size_t)std::max(1, in->tipCount) * in->Ppad);
+    if (ok) {
+        // every partials buffer the caller may address, else (memory-tight) all but the compact tips
+        int want[2] = {in->nPartials, std::max(1, in->nPartials - std::min(in->nCompact, in->tipCount))};
+        for (int attempt = 0; attempt < 2 && in->partialsBase == nullptr; ++attempt) {
+            size_t bytes = (size_t)want[attempt] * in->partialsElems * sizeof(double);
+            if (cudaMalloc(reinterpret_cast<void**>(&in->partialsBase), bytes) == cudaSuccess) in->nSlots = want[attempt];
+            else { cudaGetLastError(); in->partialsBase = nullptr; }
+        }
+        if (in->partialsBase == nullptr) { destroyInstance(in); return BEAGLE_ERROR_OUT_OF_MEMORY; }
+    }
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&in->hStage), in->stageSize) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&in->hOut), 1024 * sizeof(double)) == cudaSuccess;
     if (ok) {
@@ -536,15 +554,14 @@ int beagleSetTipStates(int instance, int tipIndex, const int* inStates) {
         s32[p] = s;
         s8[p] = (uint8_t)s;
     }
-    if (in->states32[tipIndex] == nullptr) {
-        in->states32[tipIndex] = static_cast<int*>(slabAlloc(in, sizeof(int) * in->Ppad));
-        in->states8[tipIndex] = static_cast<uint8_t*>(slabAlloc(in, in->Ppad));
-        if (in->states32[tipIndex] == nullptr || in->states8[tipIndex] == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
-    }
+    if (tipIndex >= in->tipCount) return BEAGLE_ERROR_OUT_OF_RANGE;
+    in->states32[tipIndex] = in->states32Base + (size_t)tipIndex * in->Ppad;
+    in->states8[tipIndex] = in->states8Base + (size_t)tipIndex * in->Ppad;
     CUDA_OK(cudaMemcpyAsync(in->states32[tipIndex], s32.data(), sizeof(int) * in->Ppad, cudaMemcpyHostToDevice, in->stream));
     CUDA_OK(cudaMemcpyAsync(in->states8[tipIndex], s8.data(), in->Ppad, cudaMemcpyHostToDevice, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
-    in->partials[tipIndex] = nullptr;       // the buffer is a compact tip from now on
+    // the buffer is a compact tip from now on (states32[idx] != nullptr marks it; a previously assigned
+    // partials slot stays reserved)
     return BEAGLE_SUCCESS;
 }
 
@@ -722,15 +739,20 @@ int beagleUpdateTransitionMatricesWithMultipleModels(int instance, const int* ei
     return updateMatricesImpl(in, eigenIndices, 0, categoryRateIndices, probabilityIndices, edgeLengths, count);
 }
 
+// device index of P[c][i][j] inside one matrix buffer (transposed; 4-state path: [j][CP][i])
+static inline size_t matIndex(const Instance* in, int c, int i, int j) {
+    return in->matCP ? ((size_t)j * in->matCP + c) * 4 + i : ((size_t)c * in->Sp + j) * in->Sp + i;
+}
+
 int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMatrix, double) {
     GET_INSTANCE(in, instance);
     if (!validRange(matrixIndex, in->nMatrices)) return BEAGLE_ERROR_OUT_OF_RANGE;
-    const size_t n = (size_t)in->C * in->Sp * in->Sp;
+    const size_t n = in->matStride;
     std::vector<double> t(n, 0.0);
     for (int c = 0; c < in->C; ++c)
         for (int i = 0; i < in->S; ++i)
             for (int j = 0; j < in->S; ++j)
-                t[((size_t)c * in->Sp + j) * in->Sp + i] = inMatrix[((size_t)c * in->S + i) * in->S + j];
+                t[matIndex(in, c, i, j)] = inMatrix[((size_t)c * in->S + i) * in->S + j];
     CUDA_OK(cudaMemcpyAsync(in->dMat + matrixIndex * n, t.data(), sizeof(double) * n, cudaMemcpyHostToDevice, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
     return BEAGLE_SUCCESS;
@@ -739,14 +761,14 @@ int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMat
 int beagleGetTransitionMatrix(int instance, int matrixIndex, double* outMatrix) {
     GET_INSTANCE(in, instance);
     if (!validRange(matrixIndex, in->nMatrices)) return BEAGLE_ERROR_OUT_OF_RANGE;
-    const size_t n = (size_t)in->C * in->Sp * in->Sp;
+    const size_t n = in->matStride;
     std::vector<double> t(n);
     CUDA_OK(cudaMemcpyAsync(t.data(), in->dMat + matrixIndex * n, sizeof(double) * n, cudaMemcpyDeviceToHost, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
     for (int c = 0; c < in->C; ++c)
         for (int i = 0; i < in->S; ++i)
             for (int j = 0; j < in->S; ++j)
-                outMatrix[((size_t)c * in->S + i) * in->S + j] = t[((size_t)c * in->Sp + j) * in->Sp + i];
+                outMatrix[((size_t)c * in->S + i) * in->S + j] = t[matIndex(in, c, i, j)];
     return BEAGLE_SUCCESS;
 }
 

@@ -32,6 +32,19 @@ struct alignas(16) DevOp {
     int pad_;
 };
 
+// Compact operation record of the 4-state walk: 48 bytes = three warp-uniform 128-bit loads, all
+// addressing by index so that no pointer has to be chased on the per-op critical path.
+//   dest/c1/c2 : partials slot (>= 0) in the contiguous slab, or -(tipIndex+1) for a compact tip
+//   m1/m2      : transition-matrix buffer index;  sw/sr/cum : scale buffer index or -1
+//   slots      : byte0 srcSlot1, byte1 srcSlot2, byte2 dstSlot of the shared-memory operand stack (0xFF = none)
+struct alignas(16) Op4 {
+    int dest, c1, c2, m1;
+    int m2, sw, sr, cum;
+    int pBegin, pEnd;
+    unsigned int slots;
+    int pad_;
+};
+
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
 
 struct Instance {
@@ -44,13 +57,17 @@ struct Instance {
     int smCount = 148;
     size_t maxSmemOptin = 0;
 
-    size_t partialsElems = 0;                 // C*Ppad*Sp
-    std::vector<double*> partials;            // lazily allocated, one per buffer index
-    std::vector<uint8_t*> states8;
+    size_t partialsElems = 0;                 // C*Ppad*Sp = stride of one partials slot
+    double* partialsBase = nullptr;           // ONE contiguous slab of nSlots partials buffers
+    int nSlots = 0, nextSlot = 0;
+    std::vector<int> slotOf;                  // buffer index -> slot (assigned on first use), -1 = none
+    std::vector<double*> partials;            // = partialsBase + slot*stride, nullptr while unassigned
+    uint8_t* states8Base = nullptr;           // [tipCount][Ppad] compact states (4-state path)
+    int* states32Base = nullptr;              // [tipCount][Ppad] compact states (generic path)
+    std::vector<uint8_t*> states8;            // non-null while buffer idx is a compact tip
     std::vector<int*> states32;
-    std::vector<void*> slabs;                 // backing allocations handed out by the bump allocator
-    char* slabCur = nullptr;
-    size_t slabLeft = 0;
+    int matCP = 0;                            // 4-state matrix layout [j][CP][i] (CP = padded categories), 0 = [c][j][i]
+    size_t matStride = 0;                     // elements per transition-matrix buffer
 
     double* dEigen = nullptr;                 // [nEigen][2*S*S + 2*S]
     double* dMat = nullptr;                   // [nMatrices][C][Sp][Sp] transposed
@@ -81,15 +98,17 @@ struct Instance {
     long timedLaunches[T_CLASSES] = {0, 0, 0};
 
     // tuning knobs (environment overridable, see api.cu)
+    size_t walkSmemConfigured = 0;
     int walkBlock = 64;
     int walkVariant = 0;
     int reorder = 1;
+    int stackDepthMax = 12;
 };
 
 // ---- kernel launchers (kernels.cu) -----------------------------------------------------------
 cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const int* dEigenIdx,
                                      const int* dRateSet, const double* dLengths, int count);
-cudaError_t launchWalk4(Instance* in, const DevOp* dOps, int nOps, int stackDepth);
+cudaError_t launchWalk4(Instance* in, const Op4* dOps, int nOps, int stackDepth);
 cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, int nOps);
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
                        const double* cumScale, int pBegin, int pEnd, double* dOutSlot);

@@ -46,7 +46,7 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
                              int complexForm, const double* __restrict__ ratesBase,
                              const int* __restrict__ probIdx, const int* __restrict__ eigenIdx,
                              const int* __restrict__ rateSet, const double* __restrict__ lengths,
-                             double* __restrict__ matBase) {
+                             double* __restrict__ matBase, size_t matStride, int matCP) {
     extern __shared__ double sm[];
     double* ec = sm;
     double* ss = sm + S;
@@ -76,7 +76,9 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
         }
     }
     __syncthreads();
-    double* out = matBase + ((size_t)probIdx[b] * C + c) * Sp * Sp;
+    // generic layout [c][j][i]; 4-state layout [j][CP][i] (one 128-byte line holds row j of all categories)
+    double* out = matBase + (size_t)probIdx[b] * matStride + (matCP ? (size_t)c * 4 : (size_t)c * Sp * Sp);
+    const int rowStride = matCP ? matCP * 4 : Sp;
     for (int idx = threadIdx.x; idx < Sp * Sp; idx += blockDim.x) {
         int j = idx / Sp, i = idx % Sp;          // out[j][i] = P[i][j]
         double acc = 0.0;
@@ -87,7 +89,7 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
             }
             acc = fabs(acc);
         }
-        out[idx] = acc;
+        out[(size_t)j * rowStride + i] = acc;
     }
 }
 
@@ -99,7 +101,8 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
     dim3 grid(count, in->C);
     k_transition<<<grid, threads, smem, in->stream>>>(in->dEigen, 2 * (size_t)in->S * in->S + 2 * in->S, in->S,
                                                       in->Sp, in->C, in->complexEigen ? 1 : 0, in->dRates,
-                                                      dProbIdx, dEigenIdx, dRateSet, dLengths, in->dMat);
+                                                      dProbIdx, dEigenIdx, dRateSet, dLengths, in->dMat,
+                                                      in->matStride, in->matCP);
     return cudaGetLastError();
 }
 
@@ -108,95 +111,142 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
 // ---------------------------------------------------------------------------------------------
 // Warp layout: CP categories (power of two >= C) x G = 32/CP consecutive patterns.  lane = c*G + g.
 // Each thread owns the 4 states of one (pattern, category) cell = 32 contiguous bytes in [C][Ppad][4].
-// STACK: per-thread operand stack in shared memory, slot s of thread t split into two 16-byte halves
-//        laid out [slot][half][thread] so that every LDS.128/STS.128 is bank-conflict free.
+// Per op and warp the L1/LSU wavefront budget is what bounds this kernel once HBM writes are the only
+// DRAM traffic, so every access is shaped to touch the fewest 128-byte lines:
+//   * op record: 48 B, warp-uniform, three 128-bit loads, fetched ONE OP AHEAD (off the critical path)
+//   * matrices : layout [j][CP][i] -> row j of all categories is one 128-byte line, 4 loads per child
+//   * children produced earlier in the same list: per-thread operand stack in shared memory,
+//     laid out [slot][half][thread] so every LDS.128/STS.128 is bank-conflict free
+//   * tip states: one byte per pattern, fetched one op ahead
+struct WalkArgs {
+    const Op4* ops;
+    int nOps;
+    double* partials;          // slab base
+    size_t stride;             // elements per slot
+    const uint8_t* states;     // [tip][Ppad]
+    const double* mats;        // [matrix][4][CP][4]
+    double* scale;             // [buffer][Ppad]
+    int S, C, Ppad, logScalers;
+};
+
+__device__ __forceinline__ Op4 loadOp(const Op4* p) {
+    const int4* q = reinterpret_cast<const int4*>(p);
+    int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    Op4 o;
+    o.dest = a.x; o.c1 = a.y; o.c2 = a.z; o.m1 = a.w;
+    o.m2 = b.x; o.sw = b.y; o.sr = b.z; o.cum = b.w;
+    o.pBegin = c.x; o.pEnd = c.y; o.slots = (unsigned)c.z; o.pad_ = c.w;
+    return o;
+}
+
+// non-volatile: a read-only load the scheduler may hoist freely
+__device__ __forceinline__ void ldg256_ro(const double* p, double (&v)[4]) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+        : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+struct Mat4 { double r[4][4]; };     // r[j][i] = P[i][j] of this thread's category
+
+template <int CP>
+__device__ __forceinline__ void loadMat(const double* __restrict__ mats, int idx, int moff, Mat4& M) {
+    const double* m = mats + (size_t)idx * (16 * CP) + moff;
+    ldg256_ro(m, M.r[0]); ldg256_ro(m + 4 * CP, M.r[1]); ldg256_ro(m + 8 * CP, M.r[2]); ldg256_ro(m + 12 * CP, M.r[3]);
+}
+
+__device__ __forceinline__ void applyMat(const Mat4& M, const double (&x)[4], double (&y)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = M.r[0][i] * x[0] + M.r[1][i] * x[1] + M.r[2][i] * x[2] + M.r[3][i] * x[3];
+}
+
+// compact tip: column `s` of P (register select, no dependent load); gap/unknown -> 1
+__device__ __forceinline__ void tipColumn(const Mat4& M, int s, int S, double (&y)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double v = (i < S) ? 1.0 : 0.0;
+        v = (s == 0) ? M.r[0][i] : v;
+        v = (s == 1) ? M.r[1][i] : v;
+        v = (s == 2) ? M.r[2][i] : v;
+        v = (s == 3) ? M.r[3][i] : v;
+        y[i] = v;
+    }
+}
+
+// Software pipeline (all read-only operands are off the dependent chain):
+//   iteration k computes op k from registers; meanwhile the matrices + tip states of op k+1 and the
+//   record of op k+2 are in flight.
 template <int CP, bool STACK>
 __global__ void __launch_bounds__(256)
-k_walk4(const DevOp* __restrict__ ops, int nOps, int S, int C, int Ppad, int logScalers) {
+k_walk4(const WalkArgs A) {
     constexpr int G = 32 / CP;
     extern __shared__ double2 stackMem[];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int c = lane / G;
     const int p = warp * G + (lane % G);
-    const bool cellValid = (c < C) && (p < Ppad);
-    const size_t off = ((size_t)(cellValid ? c : 0) * Ppad + (cellValid ? p : 0)) * 4;
-    const size_t moff = (size_t)(cellValid ? c : 0) * 16;
+    const bool cellValid = (c < A.C) && (p < A.Ppad);
+    const int cc = cellValid ? c : 0, pp = cellValid ? p : 0;
+    const size_t off = ((size_t)cc * A.Ppad + pp) * 4;
+    const int moff = cc * 4;
     const int nthreads = blockDim.x;
+    const int S = A.S;
+    const int last = A.nOps - 1;
 
-    for (int k = 0; k < nOps; ++k) {
-        // the op record is warp-uniform: fetched through the read-only path, broadcast by L1
-        const DevOp* op = ops + k;
-        const double* c1 = op->c1;
-        const double* c2 = op->c2;
-        const int4 rng = *reinterpret_cast<const int4*>(&op->pBegin);   // pBegin,pEnd,srcSlot1,srcSlot2
-        const int dstSlot = op->dstSlot;
-        const bool active = cellValid && p >= rng.x && p < rng.y;
+    Op4 cur = loadOp(A.ops);
+    Op4 nxt = loadOp(A.ops + min(1, last));
+    Mat4 M1, M2;
+    loadMat<CP>(A.mats, cur.m1, moff, M1);
+    loadMat<CP>(A.mats, cur.m2, moff, M2);
+    int st1 = S, st2 = S;
+    if (cur.c1 < 0) st1 = __ldg(A.states + (size_t)(-cur.c1 - 1) * A.Ppad + pp);
+    if (cur.c2 < 0) st2 = __ldg(A.states + (size_t)(-cur.c2 - 1) * A.Ppad + pp);
+
+    for (int k = 0; k <= last; ++k) {
+        // ---- prefetch: record of op k+2, matrices and tip states of op k+1 ---------------------------
+        const Op4 nn = loadOp(A.ops + min(k + 2, last));
+        Mat4 N1, N2;
+        loadMat<CP>(A.mats, nxt.m1, moff, N1);
+        loadMat<CP>(A.mats, nxt.m2, moff, N2);
+        int nst1 = S, nst2 = S;
+        if (nxt.c1 < 0) nst1 = __ldg(A.states + (size_t)(-nxt.c1 - 1) * A.Ppad + pp);
+        if (nxt.c2 < 0) nst2 = __ldg(A.states + (size_t)(-nxt.c2 - 1) * A.Ppad + pp);
+
+        const bool active = cellValid && p >= cur.pBegin && p < cur.pEnd;
+        const int s1 = cur.slots & 0xFF, s2 = (cur.slots >> 8) & 0xFF, sd = (cur.slots >> 16) & 0xFF;
 
         double a[4], b[4], d[4];
         // ---- child 1 ------------------------------------------------------------------------
-        {
-            const double* m = op->m1 + moff;
-            if (STACK && rng.z >= 0) {
-                double2 lo = stackMem[(rng.z * 2 + 0) * nthreads + threadIdx.x];
-                double2 hi = stackMem[(rng.z * 2 + 1) * nthreads + threadIdx.x];
-                double x[4] = {lo.x, lo.y, hi.x, hi.y};
-                double r0[4], r1[4], r2[4], r3[4];
-                ldg256_nc(m, r0); ldg256_nc(m + 4, r1); ldg256_nc(m + 8, r2); ldg256_nc(m + 12, r3);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = r0[i] * x[0] + r1[i] * x[1] + r2[i] * x[2] + r3[i] * x[3];
-            } else if (c1 != nullptr) {
-                double x[4];
-                if (active) ldg256(c1 + off, x); else { x[0] = x[1] = x[2] = x[3] = 0.0; }
-                double r0[4], r1[4], r2[4], r3[4];
-                ldg256_nc(m, r0); ldg256_nc(m + 4, r1); ldg256_nc(m + 8, r2); ldg256_nc(m + 12, r3);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = r0[i] * x[0] + r1[i] * x[1] + r2[i] * x[2] + r3[i] * x[3];
-            } else {
-                const uint8_t* st = static_cast<const uint8_t*>(op->s1);
-                int s = active ? (int)__ldg(st + p) : S;
-                if (s < S) { ldg256_nc(m + 4 * s, a); }
-                else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = (i < S) ? 1.0 : 0.0;
-                }
-            }
+        if (cur.c1 < 0) {
+            tipColumn(M1, active ? st1 : S, S, a);
+        } else {
+            double x[4];
+            if (STACK && s1 != 0xFF) {
+                double2 lo = stackMem[(s1 * 2 + 0) * nthreads + threadIdx.x];
+                double2 hi = stackMem[(s1 * 2 + 1) * nthreads + threadIdx.x];
+                x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
+            } else if (active) {
+                ldg256(A.partials + (size_t)cur.c1 * A.stride + off, x);
+            } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
+            applyMat(M1, x, a);
         }
         // ---- child 2 ------------------------------------------------------------------------
-        {
-            const double* m = op->m2 + moff;
-            if (STACK && rng.w >= 0) {
-                double2 lo = stackMem[(rng.w * 2 + 0) * nthreads + threadIdx.x];
-                double2 hi = stackMem[(rng.w * 2 + 1) * nthreads + threadIdx.x];
-                double x[4] = {lo.x, lo.y, hi.x, hi.y};
-                double r0[4], r1[4], r2[4], r3[4];
-                ldg256_nc(m, r0); ldg256_nc(m + 4, r1); ldg256_nc(m + 8, r2); ldg256_nc(m + 12, r3);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) b[i] = r0[i] * x[0] + r1[i] * x[1] + r2[i] * x[2] + r3[i] * x[3];
-            } else if (c2 != nullptr) {
-                double x[4];
-                if (active) ldg256(c2 + off, x); else { x[0] = x[1] = x[2] = x[3] = 0.0; }
-                double r0[4], r1[4], r2[4], r3[4];
-                ldg256_nc(m, r0); ldg256_nc(m + 4, r1); ldg256_nc(m + 8, r2); ldg256_nc(m + 12, r3);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) b[i] = r0[i] * x[0] + r1[i] * x[1] + r2[i] * x[2] + r3[i] * x[3];
-            } else {
-                const uint8_t* st = static_cast<const uint8_t*>(op->s2);
-                int s = active ? (int)__ldg(st + p) : S;
-                if (s < S) { ldg256_nc(m + 4 * s, b); }
-                else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) b[i] = (i < S) ? 1.0 : 0.0;
-                }
-            }
+        if (cur.c2 < 0) {
+            tipColumn(M2, active ? st2 : S, S, b);
+        } else {
+            double x[4];
+            if (STACK && s2 != 0xFF) {
+                double2 lo = stackMem[(s2 * 2 + 0) * nthreads + threadIdx.x];
+                double2 hi = stackMem[(s2 * 2 + 1) * nthreads + threadIdx.x];
+                x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
+            } else if (active) {
+                ldg256(A.partials + (size_t)cur.c2 * A.stride + off, x);
+            } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
+            applyMat(M2, x, b);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[i] = a[i] * b[i];
 
         // ---- rescaling (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE) ---------
-        double* sw = op->scaleWrite;
-        const double* sr = op->scaleRead;
-        if (sw != nullptr) {
+        if (cur.sw >= 0) {
             double m = active ? fmax(fmax(d[0], d[1]), fmax(d[2], d[3])) : 0.0;
 #pragma unroll
             for (int sh = G; sh < 32; sh <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, sh));
@@ -206,55 +256,61 @@ k_walk4(const DevOp* __restrict__ ops, int nOps, int S, int C, int Ppad, int log
             for (int i = 0; i < 4; ++i) d[i] *= inv;
             if (active && c == 0) {
                 const double lm = log(m);
-                sw[p] = logScalers ? lm : m;
-                double* cum = op->cumScale;
-                if (cum != nullptr) cum[p] += lm;
+                A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
+                if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
             }
             __syncwarp();
-        } else if (sr != nullptr) {
-            double f = active ? sr[p] : 1.0;
-            if (logScalers) f = exp(f);
+        } else if (cur.sr >= 0) {
+            double f = active ? A.scale[(size_t)cur.sr * A.Ppad + p] : 1.0;
+            if (A.logScalers) f = exp(f);
             const double inv = 1.0 / f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) d[i] *= inv;
         }
 
-        if (active) stg256(op->dest + off, d);
-        if (STACK && dstSlot >= 0) {
-            stackMem[(dstSlot * 2 + 0) * nthreads + threadIdx.x] = make_double2(d[0], d[1]);
-            stackMem[(dstSlot * 2 + 1) * nthreads + threadIdx.x] = make_double2(d[2], d[3]);
+        if (active) stg256(A.partials + (size_t)cur.dest * A.stride + off, d);
+        if (STACK && sd != 0xFF) {
+            stackMem[(sd * 2 + 0) * nthreads + threadIdx.x] = make_double2(d[0], d[1]);
+            stackMem[(sd * 2 + 1) * nthreads + threadIdx.x] = make_double2(d[2], d[3]);
         }
+        cur = nxt; nxt = nn; M1 = N1; M2 = N2; st1 = nst1; st2 = nst2;
     }
 }
 
 template <int CP>
-static cudaError_t launchWalk4T(Instance* in, const DevOp* dOps, int nOps, int stackDepth) {
+static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, int nOps, int stackDepth) {
     constexpr int G = 32 / CP;
     const int warps = (in->Ppad + G - 1) / G;
     const int wpb = in->walkBlock / 32;
     const int blocks = (warps + wpb - 1) / wpb;
-    const int log = in->logScalers ? 1 : 0;
+    WalkArgs A;
+    A.ops = dOps; A.nOps = nOps; A.partials = in->partialsBase; A.stride = in->partialsElems;
+    A.states = in->states8Base; A.mats = in->dMat; A.scale = in->dScale;
+    A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.logScalers = in->logScalers ? 1 : 0;
     if (stackDepth > 0) {
         size_t smem = (size_t)stackDepth * 32 * in->walkBlock;
-        static bool attrSet[4] = {false, false, false, false};
-        (void)attrSet;
-        cudaFuncSetAttribute(k_walk4<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_walk4<CP, true><<<blocks, in->walkBlock, smem, in->stream>>>(dOps, nOps, in->S, in->C, in->Ppad, log);
+        if (smem > in->walkSmemConfigured) {
+            cudaError_t e = cudaFuncSetAttribute(k_walk4<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            in->walkSmemConfigured = smem;
+        }
+        k_walk4<CP, true><<<blocks, in->walkBlock, smem, in->stream>>>(A);
     } else {
-        k_walk4<CP, false><<<blocks, in->walkBlock, 0, in->stream>>>(dOps, nOps, in->S, in->C, in->Ppad, log);
+        k_walk4<CP, false><<<blocks, in->walkBlock, 0, in->stream>>>(A);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launchWalk4(Instance* in, const DevOp* dOps, int nOps, int stackDepth) {
+cudaError_t launchWalk4(Instance* in, const Op4* dOps, int nOps, int stackDepth) {
     if (nOps <= 0) return cudaSuccess;
-    const int C = in->C;
-    if (C <= 1) return launchWalk4T<1>(in, dOps, nOps, stackDepth);
-    if (C <= 2) return launchWalk4T<2>(in, dOps, nOps, stackDepth);
-    if (C <= 4) return launchWalk4T<4>(in, dOps, nOps, stackDepth);
-    if (C <= 8) return launchWalk4T<8>(in, dOps, nOps, stackDepth);
-    if (C <= 16) return launchWalk4T<16>(in, dOps, nOps, stackDepth);
-    return launchWalk4T<32>(in, dOps, nOps, stackDepth);
+    switch (in->matCP) {
+        case 1: return launchWalk4T<1>(in, dOps, nOps, stackDepth);
+        case 2: return launchWalk4T<2>(in, dOps, nOps, stackDepth);
+        case 4: return launchWalk4T<4>(in, dOps, nOps, stackDepth);
+        case 8: return launchWalk4T<8>(in, dOps, nOps, stackDepth);
+        case 16: return launchWalk4T<16>(in, dOps, nOps, stackDepth);
+        default: return launchWalk4T<32>(in, dOps, nOps, stackDepth);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
