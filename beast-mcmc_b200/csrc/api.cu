@@ -179,54 +179,88 @@ char gImplDesc[] = "sm_100a walk kernels: one launch per operation list, shared-
 // ---- op planning ------------------------------------------------------------------------------
 struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; };
 
-// Dependency-safe re-ordering (Sethi-Ullman: deeper-need subtree first) so that the number of
-// simultaneously live intermediate results -- operand-stack slots -- is minimal, and slot
-// assignment.  Any topological order is valid because pattern columns never interact.
-void planOrder(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder, std::vector<int>& order) {
+// Execution plan of one operation list.
+//
+// Pattern columns never interact, so ANY topological order of the list is valid, and independent
+// subtrees of the list may run concurrently.  The plan cuts the op forest into PHASES of disjoint
+// subtrees of at most T ops ("all maximal subtrees with <= T ops", then recurse on what is left):
+//   * every (subtree, pattern tile) pair is one independent walk -> grid.y = subtrees of the phase,
+//     which multiplies the warps in flight (latency hiding) and shortens the dependent chain from
+//     n ops to ~phases*T;
+//   * inside a subtree ops run in Sethi-Ullman order (deeper-need child first), which minimises the
+//     number of live intermediate results = operand-stack slots;
+//   * results crossing a phase boundary go through global memory (L2), everything else through the
+//     shared-memory stack.
+// Lists with hazards the forest model does not cover (a buffer written twice, read-before-write,
+// a result consumed by two ops) run as ONE subtree in the caller's order.
+struct Sub { int begin, end; };
+struct Plan {
+    std::vector<int> order;          // execution position -> index into the caller's list
+    std::vector<Sub> subs;           // position ranges, grouped by phase
+    std::vector<int> phaseStart;     // index into subs; size = phases + 1
+};
+
+void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder, int T, Plan& plan) {
     const int n = (int)ops.size();
-    order.resize(n);
-    for (int k = 0; k < n; ++k) order[k] = k;
-    if (!allowReorder || n < 3) return;
+    auto single = [&]() {
+        plan.order.resize(n);
+        for (int k = 0; k < n; ++k) plan.order[k] = k;
+        plan.subs.assign(1, Sub{0, n});
+        plan.phaseStart = {0, 1};
+    };
+    if (!allowReorder || n < 2) { single(); return; }
     std::vector<int> writer(nBuffers, -1);
     for (int k = 0; k < n; ++k) {
-        if (writer[ops[k].dest] >= 0) return;           // double write: keep the caller's order
+        if (writer[ops[k].dest] >= 0) { single(); return; }
         writer[ops[k].dest] = k;
     }
-    std::vector<int> ch0(n, -1), ch1(n, -1), consumed(n, 0), need(n, 1);
+    std::vector<int> ch0(n, -1), ch1(n, -1), parent(n, -1);
     for (int k = 0; k < n; ++k) {
         const int a = writer[ops[k].c1], b = writer[ops[k].c2];
-        if (a >= 0) { if (a >= k) return; ch0[k] = a; consumed[a]++; }
-        if (b >= 0 && ops[k].c2 != ops[k].c1) { if (b >= k) return; ch1[k] = b; consumed[b]++; }
-        // scale buffers: a later op reading a scale buffer written earlier keeps its relative order
-        // automatically when it is an ancestor; otherwise (never issued by BEAST) bail out.
-        int na = ch0[k] >= 0 ? need[ch0[k]] : 0, nb = ch1[k] >= 0 ? need[ch1[k]] : 0;
-        if (na < nb) std::swap(na, nb);
-        need[k] = std::max(1, std::max(na, nb + (nb > 0 ? 1 : 0)));
-        if (consumed[k] > 1) return;                    // DAG, not a forest: keep the caller's order
+        if (a >= 0) { if (a >= k || parent[a] >= 0) { single(); return; } ch0[k] = a; parent[a] = k; }
+        if (b >= 0 && ops[k].c2 != ops[k].c1) { if (b >= k || parent[b] >= 0) { single(); return; } ch1[k] = b; parent[b] = k; }
+        if (ops[k].dest == ops[k].c1 || ops[k].dest == ops[k].c2) { single(); return; }
     }
-    for (int k = 0; k < n; ++k) if (consumed[k] > 1) return;
-    std::vector<int> out;
-    out.reserve(n);
-    std::vector<char> seen(n, 0);
+    std::vector<char> alive(n, 1);
+    std::vector<int> size(n), need(n);
     std::vector<std::pair<int, int>> stack;
-    for (int r = 0; r < n; ++r) {
-        if (consumed[r] != 0) continue;
-        stack.push_back({r, 0});
-        while (!stack.empty()) {
-            auto [k, stageNo] = stack.back();
-            stack.pop_back();
-            if (stageNo == 1) { out.push_back(k); continue; }
-            if (seen[k]) continue;
-            seen[k] = 1;
-            stack.push_back({k, 1});
-            int a = ch0[k], b = ch1[k];
-            int na = a >= 0 ? need[a] : -1, nb = b >= 0 ? need[b] : -1;
-            // the child pushed LAST is visited FIRST: visit the larger need first
-            if (na >= nb) { if (b >= 0) stack.push_back({b, 0}); if (a >= 0) stack.push_back({a, 0}); }
-            else          { if (a >= 0) stack.push_back({a, 0}); if (b >= 0) stack.push_back({b, 0}); }
+    plan.order.clear(); plan.order.reserve(n);
+    plan.subs.clear(); plan.phaseStart.assign(1, 0);
+    int remaining = n;
+    while (remaining > 0) {
+        for (int k = 0; k < n; ++k) {
+            if (!alive[k]) continue;
+            const int a = (ch0[k] >= 0 && alive[ch0[k]]) ? ch0[k] : -1;
+            const int b = (ch1[k] >= 0 && alive[ch1[k]]) ? ch1[k] : -1;
+            size[k] = 1 + (a >= 0 ? size[a] : 0) + (b >= 0 ? size[b] : 0);
+            int na = a >= 0 ? need[a] : 0, nb = b >= 0 ? need[b] : 0;
+            if (na < nb) std::swap(na, nb);
+            need[k] = std::max(1, std::max(na, nb + (nb > 0 ? 1 : 0)));
         }
+        for (int r = 0; r < n; ++r) {
+            if (!alive[r] || size[r] > T) continue;
+            if (parent[r] >= 0 && size[parent[r]] <= T) continue;       // not maximal
+            const int begin = (int)plan.order.size();
+            stack.push_back({r, 0});
+            while (!stack.empty()) {
+                auto [k, stageNo] = stack.back();
+                stack.pop_back();
+                if (stageNo == 1) { plan.order.push_back(k); continue; }
+                stack.push_back({k, 1});
+                const int a = (ch0[k] >= 0 && alive[ch0[k]]) ? ch0[k] : -1;
+                const int b = (ch1[k] >= 0 && alive[ch1[k]]) ? ch1[k] : -1;
+                const int na = a >= 0 ? need[a] : -1, nb = b >= 0 ? need[b] : -1;
+                // the child pushed LAST is visited FIRST: visit the larger need first
+                if (na >= nb) { if (b >= 0) stack.push_back({b, 0}); if (a >= 0) stack.push_back({a, 0}); }
+                else          { if (a >= 0) stack.push_back({a, 0}); if (b >= 0) stack.push_back({b, 0}); }
+            }
+            plan.subs.push_back(Sub{begin, (int)plan.order.size()});
+        }
+        // retire this phase's ops only now, so that maximality was judged on a consistent snapshot
+        for (int q = plan.subs[plan.phaseStart.back()].begin; q < (int)plan.order.size(); ++q) alive[plan.order[q]] = 0;
+        remaining = n - (int)plan.order.size();
+        plan.phaseStart.push_back((int)plan.subs.size());
     }
-    if ((int)out.size() == n) order.swap(out);
 }
 
 int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartition) {
@@ -251,27 +285,48 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         if (in->partials[o.c2] == nullptr && in->states32[o.c2] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
     }
     const bool fourState = in->matCP > 0;
-    std::vector<int> order;
-    planOrder(hops, in->nBuffers, in->reorder && !byPartition, order);
+    Plan plan;
+    {
+        int T = in->phaseT;
+        if (T <= 0) {
+            // enough (subtree x tile) walks to put ~32 warps on every SM, 4x oversubscribed for balance
+            const int cellsPerWarp = fourState ? (32 / in->matCP) * in->walkR : 1;
+            const int warpsPerSub = fourState ? (in->Ppad + cellsPerWarp - 1) / cellsPerWarp : std::max(1, in->Ppad / 4);
+            const int wantSubs = std::max(1, 4 * ((in->smCount * 32 + warpsPerSub - 1) / warpsPerSub));
+            T = std::max(8, (n + wantSubs - 1) / wantSubs);
+        }
+        planPhases(hops, in->nBuffers, in->reorder && !byPartition, T, plan);
+    }
+    const std::vector<int>& order = plan.order;
 
     // ---- stack slots (4-state path only): one backward pass finds, for every produced value, the
     // position of its LAST reader inside this list (before the buffer is re-written); the forward
     // pass then parks results in slots and frees each slot at that last read.
     const int maxDepth = (fourState && !byPartition && in->walkVariant >= 1) ? in->stackDepthMax : 0;
     std::vector<int> lastReadOfProd(maxDepth > 0 ? n : 0, -1);
+    std::vector<int> subOfPos(n, 0);
+    for (int sIdx = 0; sIdx < (int)plan.subs.size(); ++sIdx)
+        for (int q = plan.subs[sIdx].begin; q < plan.subs[sIdx].end; ++q) subOfPos[q] = sIdx;
     if (maxDepth > 0) {
+        // per subtree: the stack is private to a (subtree, tile) walk
         std::vector<int> lastRead(in->nBuffers, -1);
-        for (int pos = n - 1; pos >= 0; --pos) {
-            const HostOp& o = hops[order[pos]];
-            lastReadOfProd[pos] = lastRead[o.dest];
-            lastRead[o.dest] = -1;
-            if (lastRead[o.c1] < 0) lastRead[o.c1] = pos;
-            if (lastRead[o.c2] < 0) lastRead[o.c2] = pos;
+        for (const Sub& sb : plan.subs) {
+            for (int pos = sb.end - 1; pos >= sb.begin; --pos) {
+                const HostOp& o = hops[order[pos]];
+                lastReadOfProd[pos] = lastRead[o.dest];
+                lastRead[o.dest] = -1;
+                if (lastRead[o.c1] < 0) lastRead[o.c1] = pos;
+                if (lastRead[o.c2] < 0) lastRead[o.c2] = pos;
+            }
+            for (int pos = sb.begin; pos < sb.end; ++pos) {      // leave no marks for the next subtree
+                const HostOp& o = hops[order[pos]];
+                lastRead[o.dest] = lastRead[o.c1] = lastRead[o.c2] = -1;
+            }
         }
     }
     std::vector<int> slotOf(maxDepth > 0 ? in->nBuffers : 0, -1), slotFreeAt(maxDepth > 0 ? in->nBuffers : 0, -1);
     std::vector<int> freeSlots;
-    int depthUsed = 0;
+    int depthUsed = 0, depthThisSub = 0, curSub = -1;
 
     const bool fourPath = in->matCP > 0;
     std::vector<DevOp> dops(fourPath ? 0 : n);
@@ -281,6 +336,11 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         const bool t1 = in->states32[o.c1] != nullptr;
         const bool t2 = in->states32[o.c2] != nullptr;
         int srcSlot1 = -1, srcSlot2 = -1, dstSlot = -1;
+        if (maxDepth > 0 && subOfPos[pos] != curSub) {      // new subtree: fresh private stack
+            curSub = subOfPos[pos];
+            freeSlots.clear();
+            depthThisSub = 0;
+        }
         if (maxDepth > 0) {
             auto take = [&](int buf, bool isTip) -> int {
                 if (isTip) return -1;
@@ -294,7 +354,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             if (lastReadOfProd[pos] > pos) {         // a later op of this list reads the result
                 int slot = -1;
                 if (!freeSlots.empty()) { slot = freeSlots.back(); freeSlots.pop_back(); }
-                else if (depthUsed < maxDepth) slot = depthUsed++;
+                else if (depthThisSub < maxDepth) { slot = depthThisSub++; depthUsed = std::max(depthUsed, depthThisSub); }
                 if (slot >= 0) { slotOf[o.dest] = slot; slotFreeAt[o.dest] = lastReadOfProd[pos]; dstSlot = slot; }
             }
         }
@@ -329,20 +389,26 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     }
     const void* hostOps = fourPath ? (const void*)ops4.data() : (const void*)dops.data();
     const size_t opBytes = (fourPath ? sizeof(Op4) : sizeof(DevOp)) * (size_t)n;
+    const size_t subBytes = sizeof(Sub) * plan.subs.size();
     void* dOps = stage(in, hostOps, opBytes);
+    void* dSubs = stage(in, plan.subs.data(), subBytes);
     void* tmp = nullptr;
-    if (dOps == nullptr) {
+    if (dOps == nullptr || dSubs == nullptr) {
         // list larger than the staging ring: one-off allocation
-        CUDA_OK(cudaMalloc(&tmp, opBytes));
-        CUDA_OK(cudaMemcpyAsync(tmp, hostOps, opBytes, cudaMemcpyHostToDevice, in->stream));
-        CUDA_OK(cudaStreamSynchronize(in->stream));
+        CUDA_OK(cudaMalloc(&tmp, opBytes + 256 + subBytes));
         dOps = tmp;
+        dSubs = static_cast<char*>(tmp) + ((opBytes + 255) & ~size_t(255));
+        CUDA_OK(cudaMemcpyAsync(dOps, hostOps, opBytes, cudaMemcpyHostToDevice, in->stream));
+        CUDA_OK(cudaMemcpyAsync(dSubs, plan.subs.data(), subBytes, cudaMemcpyHostToDevice, in->stream));
+        CUDA_OK(cudaStreamSynchronize(in->stream));
     }
-    cudaError_t e;
-    {
+    cudaError_t e = cudaSuccess;
+    for (size_t ph = 0; ph + 1 < plan.phaseStart.size() && e == cudaSuccess; ++ph) {
+        const int s0 = plan.phaseStart[ph], s1 = plan.phaseStart[ph + 1];
+        if (s1 <= s0) continue;
         TimedScope ts(in, T_PARTIALS);
-        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), n, depthUsed)
-                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), n);
+        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int2*>(dSubs) + s0, s1 - s0, depthUsed)
+                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int2*>(dSubs) + s0, s1 - s0);
     }
     if (tmp != nullptr) { cudaStreamSynchronize(in->stream); cudaFree(tmp); }
     CUDA_OK(e);
@@ -432,6 +498,9 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     if (in->walkBlock < 32 || in->walkBlock > 256 || (in->walkBlock & 31)) in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 1);
     in->reorder = envInt("B200_REORDER", 1);
+    in->phaseT = envInt("B200_PHASE_T", 0);
+    in->walkR = envInt("B200_WALK_R", 2);
+    if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4) in->walkR = 2;
     in->stackDepthMax = std::min(64, std::max(0, envInt("B200_STACK_DEPTH", 12)));
 
     cudaDeviceProp prop;

@@ -98,18 +98,20 @@ struct Instance {
     long timedLaunches[T_CLASSES] = {0, 0, 0};
 
     // tuning knobs (environment overridable, see api.cu)
-    size_t walkSmemConfigured = 0;
+    size_t walkSmemConfigured = 0, genericSmemConfigured = 0;
     int walkBlock = 64;
     int walkVariant = 0;
     int reorder = 1;
     int stackDepthMax = 12;
+    int walkR = 2;               // patterns per thread in the 4-state walk (1, 2 or 4)
+    int phaseT = 0;              // max ops per subtree walk (0 = automatic)
 };
 
 // ---- kernel launchers (kernels.cu) -----------------------------------------------------------
 cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const int* dEigenIdx,
                                      const int* dRateSet, const double* dLengths, int count);
-cudaError_t launchWalk4(Instance* in, const Op4* dOps, int nOps, int stackDepth);
-cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, int nOps);
+cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth);
+cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int2* dSubs, int nSubs);
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
                        const double* cumScale, int pBegin, int pEnd, double* dOutSlot);
 cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,

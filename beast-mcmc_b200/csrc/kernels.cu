@@ -120,7 +120,7 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
 //   * tip states: one byte per pattern, fetched one op ahead
 struct WalkArgs {
     const Op4* ops;
-    int nOps;
+    const int2* subs;          // [subtree] = (first, one-past-last) position in ops
     double* partials;          // slab base
     size_t stride;             // elements per slot
     const uint8_t* states;     // [tip][Ppad]
@@ -148,8 +148,7 @@ __device__ __forceinline__ void ldg256_ro(const double* p, double (&v)[4]) {
 struct Mat4 { double r[4][4]; };     // r[j][i] = P[i][j] of this thread's category
 
 template <int CP>
-__device__ __forceinline__ void loadMat(const double* __restrict__ mats, int idx, int moff, Mat4& M) {
-    const double* m = mats + (size_t)idx * (16 * CP) + moff;
+__device__ __forceinline__ void loadMat(const double* __restrict__ m, Mat4& M) {
     ldg256_ro(m, M.r[0]); ldg256_ro(m + 4 * CP, M.r[1]); ldg256_ro(m + 8 * CP, M.r[2]); ldg256_ro(m + 12 * CP, M.r[3]);
 }
 
@@ -158,23 +157,13 @@ __device__ __forceinline__ void applyMat(const Mat4& M, const double (&x)[4], do
     for (int i = 0; i < 4; ++i) y[i] = M.r[0][i] * x[0] + M.r[1][i] * x[1] + M.r[2][i] * x[2] + M.r[3][i] * x[3];
 }
 
-// compact tip: column `s` of P (register select, no dependent load); gap/unknown -> 1
-__device__ __forceinline__ void tipColumn(const Mat4& M, int s, int S, double (&y)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double v = (i < S) ? 1.0 : 0.0;
-        v = (s == 0) ? M.r[0][i] : v;
-        v = (s == 1) ? M.r[1][i] : v;
-        v = (s == 2) ? M.r[2][i] : v;
-        v = (s == 3) ? M.r[3][i] : v;
-        y[i] = v;
-    }
-}
-
-// Software pipeline (all read-only operands are off the dependent chain):
-//   iteration k computes op k from registers; meanwhile the matrices + tip states of op k+1 and the
-//   record of op k+2 are in flight.
-template <int CP, bool STACK>
+// grid = (pattern tiles, subtrees of this phase).  Latency is hidden by thread-level parallelism
+// (many independent (subtree, tile) walks per SM).  What bounds the kernel once DRAM only sees the
+// mandatory writes is the LSU->register-file path (128 B/clk/SM): a 4x4 matrix costs every thread
+// 128 B per child, more than the partials themselves, so each thread keeps its category's two
+// matrices in registers and re-uses them for R patterns (R = patterns per thread, strided by G so
+// that every load/store instruction still covers 8 consecutive patterns = 256 contiguous bytes).
+template <int CP, int R, bool STACK>
 __global__ void __launch_bounds__(256)
 k_walk4(const WalkArgs A) {
     constexpr int G = 32 / CP;
@@ -182,134 +171,153 @@ k_walk4(const WalkArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int c = lane / G;
-    const int p = warp * G + (lane % G);
-    const bool cellValid = (c < A.C) && (p < A.Ppad);
-    const int cc = cellValid ? c : 0, pp = cellValid ? p : 0;
-    const size_t off = ((size_t)cc * A.Ppad + pp) * 4;
+    const int p0 = warp * (G * R) + (lane % G);          // patterns p0 + r*G
+    const bool catValid = c < A.C;
+    const int cc = catValid ? c : 0;
+    const size_t off0 = ((size_t)cc * A.Ppad + p0) * 4;
     const int moff = cc * 4;
     const int nthreads = blockDim.x;
     const int S = A.S;
-    const int last = A.nOps - 1;
+    const int2 range = __ldg(A.subs + blockIdx.y);
+    const int last = range.y - 1;
 
-    Op4 cur = loadOp(A.ops);
-    Op4 nxt = loadOp(A.ops + min(1, last));
-    Mat4 M1, M2;
-    loadMat<CP>(A.mats, cur.m1, moff, M1);
-    loadMat<CP>(A.mats, cur.m2, moff, M2);
-    int st1 = S, st2 = S;
-    if (cur.c1 < 0) st1 = __ldg(A.states + (size_t)(-cur.c1 - 1) * A.Ppad + pp);
-    if (cur.c2 < 0) st2 = __ldg(A.states + (size_t)(-cur.c2 - 1) * A.Ppad + pp);
-
-    for (int k = 0; k <= last; ++k) {
-        // ---- prefetch: record of op k+2, matrices and tip states of op k+1 ---------------------------
-        const Op4 nn = loadOp(A.ops + min(k + 2, last));
-        Mat4 N1, N2;
-        loadMat<CP>(A.mats, nxt.m1, moff, N1);
-        loadMat<CP>(A.mats, nxt.m2, moff, N2);
-        int nst1 = S, nst2 = S;
-        if (nxt.c1 < 0) nst1 = __ldg(A.states + (size_t)(-nxt.c1 - 1) * A.Ppad + pp);
-        if (nxt.c2 < 0) nst2 = __ldg(A.states + (size_t)(-nxt.c2 - 1) * A.Ppad + pp);
-
-        const bool active = cellValid && p >= cur.pBegin && p < cur.pEnd;
+    Op4 cur = loadOp(A.ops + range.x);
+    for (int k = range.x; k <= last; ++k) {
+        const Op4 nxt = loadOp(A.ops + min(k + 1, last));      // one record ahead, off the dependent chain
         const int s1 = cur.slots & 0xFF, s2 = (cur.slots >> 8) & 0xFF, sd = (cur.slots >> 16) & 0xFF;
+        const double* m1 = A.mats + (size_t)cur.m1 * (16 * CP) + moff;
+        const double* m2 = A.mats + (size_t)cur.m2 * (16 * CP) + moff;
+        Mat4 M1, M2;
+        if (cur.c1 >= 0) loadMat<CP>(m1, M1);
+        if (cur.c2 >= 0) loadMat<CP>(m2, M2);
+        const uint8_t* t1 = A.states + (size_t)(cur.c1 < 0 ? -cur.c1 - 1 : 0) * A.Ppad;
+        const uint8_t* t2 = A.states + (size_t)(cur.c2 < 0 ? -cur.c2 - 1 : 0) * A.Ppad;
+        const double* x1g = A.partials + (size_t)(cur.c1 >= 0 ? cur.c1 : 0) * A.stride + off0;
+        const double* x2g = A.partials + (size_t)(cur.c2 >= 0 ? cur.c2 : 0) * A.stride + off0;
+        double* dg = A.partials + (size_t)cur.dest * A.stride + off0;
 
-        double a[4], b[4], d[4];
-        // ---- child 1 ------------------------------------------------------------------------
-        if (cur.c1 < 0) {
-            tipColumn(M1, active ? st1 : S, S, a);
-        } else {
-            double x[4];
-            if (STACK && s1 != 0xFF) {
-                double2 lo = stackMem[(s1 * 2 + 0) * nthreads + threadIdx.x];
-                double2 hi = stackMem[(s1 * 2 + 1) * nthreads + threadIdx.x];
-                x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
-            } else if (active) {
-                ldg256(A.partials + (size_t)cur.c1 * A.stride + off, x);
-            } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
-            applyMat(M1, x, a);
-        }
-        // ---- child 2 ------------------------------------------------------------------------
-        if (cur.c2 < 0) {
-            tipColumn(M2, active ? st2 : S, S, b);
-        } else {
-            double x[4];
-            if (STACK && s2 != 0xFF) {
-                double2 lo = stackMem[(s2 * 2 + 0) * nthreads + threadIdx.x];
-                double2 hi = stackMem[(s2 * 2 + 1) * nthreads + threadIdx.x];
-                x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
-            } else if (active) {
-                ldg256(A.partials + (size_t)cur.c2 * A.stride + off, x);
-            } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
-            applyMat(M2, x, b);
-        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) d[i] = a[i] * b[i];
-
-        // ---- rescaling (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE) ---------
-        if (cur.sw >= 0) {
-            double m = active ? fmax(fmax(d[0], d[1]), fmax(d[2], d[3])) : 0.0;
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r * G;
+            const bool active = catValid && p < A.Ppad && p >= cur.pBegin && p < cur.pEnd;
+            const int pc = p < A.Ppad ? p : 0;
+            double a[4], b[4], d[4];
+            // ---- child 1 --------------------------------------------------------------------
+            if (cur.c1 < 0) {
+                const int s = active ? (int)__ldg(t1 + pc) : S;
+                if (s < S) ldg256_ro(m1 + 4 * CP * s, a);
+                else {
 #pragma unroll
-            for (int sh = G; sh < 32; sh <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, sh));
-            if (m == 0.0) m = 1.0;
-            const double inv = 1.0 / m;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] *= inv;
-            if (active && c == 0) {
-                const double lm = log(m);
-                A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
-                if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
+                    for (int i = 0; i < 4; ++i) a[i] = (i < S) ? 1.0 : 0.0;
+                }
+            } else {
+                double x[4];
+                if (STACK && s1 != 0xFF) {
+                    double2 lo = stackMem[((s1 * R + r) * 2 + 0) * nthreads + threadIdx.x];
+                    double2 hi = stackMem[((s1 * R + r) * 2 + 1) * nthreads + threadIdx.x];
+                    x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
+                } else if (active) {
+                    ldg256(x1g + (size_t)r * G * 4, x);
+                } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
+                applyMat(M1, x, a);
             }
-            __syncwarp();
-        } else if (cur.sr >= 0) {
-            double f = active ? A.scale[(size_t)cur.sr * A.Ppad + p] : 1.0;
-            if (A.logScalers) f = exp(f);
-            const double inv = 1.0 / f;
+            // ---- child 2 --------------------------------------------------------------------
+            if (cur.c2 < 0) {
+                const int s = active ? (int)__ldg(t2 + pc) : S;
+                if (s < S) ldg256_ro(m2 + 4 * CP * s, b);
+                else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] *= inv;
-        }
+                    for (int i = 0; i < 4; ++i) b[i] = (i < S) ? 1.0 : 0.0;
+                }
+            } else {
+                double x[4];
+                if (STACK && s2 != 0xFF) {
+                    double2 lo = stackMem[((s2 * R + r) * 2 + 0) * nthreads + threadIdx.x];
+                    double2 hi = stackMem[((s2 * R + r) * 2 + 1) * nthreads + threadIdx.x];
+                    x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
+                } else if (active) {
+                    ldg256(x2g + (size_t)r * G * 4, x);
+                } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
+                applyMat(M2, x, b);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = a[i] * b[i];
 
-        if (active) stg256(A.partials + (size_t)cur.dest * A.stride + off, d);
-        if (STACK && sd != 0xFF) {
-            stackMem[(sd * 2 + 0) * nthreads + threadIdx.x] = make_double2(d[0], d[1]);
-            stackMem[(sd * 2 + 1) * nthreads + threadIdx.x] = make_double2(d[2], d[3]);
+            // ---- rescaling (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE) -----
+            if (cur.sw >= 0) {
+                double m = active ? fmax(fmax(d[0], d[1]), fmax(d[2], d[3])) : 0.0;
+#pragma unroll
+                for (int sh = G; sh < 32; sh <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, sh));
+                if (m == 0.0) m = 1.0;
+                const double inv = 1.0 / m;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] *= inv;
+                if (active && c == 0) {
+                    const double lm = log(m);
+                    A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
+                    if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
+                }
+                __syncwarp();
+            } else if (cur.sr >= 0) {
+                double f = active ? A.scale[(size_t)cur.sr * A.Ppad + p] : 1.0;
+                if (A.logScalers) f = exp(f);
+                const double inv = 1.0 / f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] *= inv;
+            }
+
+            if (active) stg256(dg + (size_t)r * G * 4, d);
+            if (STACK && sd != 0xFF) {
+                stackMem[((sd * R + r) * 2 + 0) * nthreads + threadIdx.x] = make_double2(d[0], d[1]);
+                stackMem[((sd * R + r) * 2 + 1) * nthreads + threadIdx.x] = make_double2(d[2], d[3]);
+            }
         }
-        cur = nxt; nxt = nn; M1 = N1; M2 = N2; st1 = nst1; st2 = nst2;
+        cur = nxt;
     }
 }
 
-template <int CP>
-static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, int nOps, int stackDepth) {
+template <int CP, int R>
+static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth) {
     constexpr int G = 32 / CP;
-    const int warps = (in->Ppad + G - 1) / G;
+    const int warps = (in->Ppad + G * R - 1) / (G * R);
     const int wpb = in->walkBlock / 32;
-    const int blocks = (warps + wpb - 1) / wpb;
+    dim3 grid((warps + wpb - 1) / wpb, nSubs);
     WalkArgs A;
-    A.ops = dOps; A.nOps = nOps; A.partials = in->partialsBase; A.stride = in->partialsElems;
+    A.ops = dOps; A.subs = dSubs; A.partials = in->partialsBase; A.stride = in->partialsElems;
     A.states = in->states8Base; A.mats = in->dMat; A.scale = in->dScale;
     A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.logScalers = in->logScalers ? 1 : 0;
     if (stackDepth > 0) {
-        size_t smem = (size_t)stackDepth * 32 * in->walkBlock;
+        size_t smem = (size_t)stackDepth * 32 * R * in->walkBlock;
         if (smem > in->walkSmemConfigured) {
-            cudaError_t e = cudaFuncSetAttribute(k_walk4<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(k_walk4<CP, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             in->walkSmemConfigured = smem;
         }
-        k_walk4<CP, true><<<blocks, in->walkBlock, smem, in->stream>>>(A);
+        k_walk4<CP, R, true><<<grid, in->walkBlock, smem, in->stream>>>(A);
     } else {
-        k_walk4<CP, false><<<blocks, in->walkBlock, 0, in->stream>>>(A);
+        k_walk4<CP, R, false><<<grid, in->walkBlock, 0, in->stream>>>(A);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launchWalk4(Instance* in, const Op4* dOps, int nOps, int stackDepth) {
-    if (nOps <= 0) return cudaSuccess;
+template <int CP>
+static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth) {
+    switch (in->walkR) {
+        case 4: return launchWalk4R<CP, 4>(in, dOps, dSubs, nSubs, stackDepth);
+        case 2: return launchWalk4R<CP, 2>(in, dOps, dSubs, nSubs, stackDepth);
+        default: return launchWalk4R<CP, 1>(in, dOps, dSubs, nSubs, stackDepth);
+    }
+}
+
+cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth) {
+    if (nSubs <= 0) return cudaSuccess;
     switch (in->matCP) {
-        case 1: return launchWalk4T<1>(in, dOps, nOps, stackDepth);
-        case 2: return launchWalk4T<2>(in, dOps, nOps, stackDepth);
-        case 4: return launchWalk4T<4>(in, dOps, nOps, stackDepth);
-        case 8: return launchWalk4T<8>(in, dOps, nOps, stackDepth);
-        case 16: return launchWalk4T<16>(in, dOps, nOps, stackDepth);
-        default: return launchWalk4T<32>(in, dOps, nOps, stackDepth);
+        case 1: return launchWalk4T<1>(in, dOps, dSubs, nSubs, stackDepth);
+        case 2: return launchWalk4T<2>(in, dOps, dSubs, nSubs, stackDepth);
+        case 4: return launchWalk4T<4>(in, dOps, dSubs, nSubs, stackDepth);
+        case 8: return launchWalk4T<8>(in, dOps, dSubs, nSubs, stackDepth);
+        case 16: return launchWalk4T<16>(in, dOps, dSubs, nSubs, stackDepth);
+        default: return launchWalk4T<32>(in, dOps, dSubs, nSubs, stackDepth);
     }
 }
 
@@ -321,7 +329,7 @@ cudaError_t launchWalk4(Instance* in, const Op4* dOps, int nOps, int stackDepth)
 // tile (thread index = pattern-major, parent state fastest: conflict-free matrix reads, broadcast
 // child reads, coalesced stores), tracks per-pattern maxima for the optional rescale.
 __global__ void __launch_bounds__(256)
-k_walk_generic(const DevOp* __restrict__ ops, int nOps, int S, int Sp, int C, int Ppad, int TP,
+k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int S, int Sp, int C, int Ppad, int TP,
                int logScalers, int stageMatrices) {
     extern __shared__ double smg[];
     const size_t msz = stageMatrices ? (size_t)Sp * Sp : 0;
@@ -333,8 +341,9 @@ k_walk_generic(const DevOp* __restrict__ ops, int nOps, int S, int Sp, int C, in
     const int p0 = blockIdx.x * TP;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int tileElems = TP * Sp;
+    const int2 range = subs[blockIdx.y];
 
-    for (int k = 0; k < nOps; ++k) {
+    for (int k = range.x; k < range.y; ++k) {
         const DevOp op = ops[k];
         const bool doMax = op.scaleWrite != nullptr;
         if (doMax) for (int q = tid; q < TP; q += nt) pmax[q] = 0ull;
@@ -413,8 +422,8 @@ k_walk_generic(const DevOp* __restrict__ ops, int nOps, int S, int Sp, int C, in
     }
 }
 
-cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, int nOps) {
-    if (nOps <= 0) return cudaSuccess;
+cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int2* dSubs, int nSubs) {
+    if (nSubs <= 0) return cudaSuccess;
     const int Sp = in->Sp;
     const size_t budget = in->maxSmemOptin > 16384 ? in->maxSmemOptin - 2048 : 46000;
     int stage = (2 * (size_t)Sp * Sp * 8 + 2 * 8 * (size_t)Sp * 8 + 64 <= budget) ? 1 : 0;
@@ -423,9 +432,13 @@ cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, int nOps) {
     while (TP > 1 && fixed + (size_t)TP * (2 * Sp + 1) * 8 > budget) TP >>= 1;
     while (TP > 8 && (in->Ppad + TP - 1) / TP < in->smCount) TP >>= 1;   // keep every SM busy
     size_t smem = fixed + (size_t)TP * (2 * Sp + 1) * 8;
-    cudaFuncSetAttribute(k_walk_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int blocks = (in->Ppad + TP - 1) / TP;
-    k_walk_generic<<<blocks, 256, smem, in->stream>>>(dOps, nOps, in->S, Sp, in->C, in->Ppad, TP,
+    if (smem > in->genericSmemConfigured) {
+        cudaError_t e = cudaFuncSetAttribute(k_walk_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        in->genericSmemConfigured = smem;
+    }
+    dim3 grid((in->Ppad + TP - 1) / TP, nSubs);
+    k_walk_generic<<<grid, 256, smem, in->stream>>>(dOps, dSubs, in->S, Sp, in->C, in->Ppad, TP,
                                                       in->logScalers ? 1 : 0, stage);
     return cudaGetLastError();
 }

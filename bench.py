@@ -406,7 +406,9 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    k_avg_ms = k_ms / max(k_n, 1)
+    # updatePartials is one launch per phase of independent subtrees; the roofline unit is the whole
+    # operation list (all its launches) of one step
+    k_avg_ms = k_ms / args.steps
     achieved = byt / (k_avg_ms * 1e-3) / 1e9
     line = dict(meta_base)
     line.update({
@@ -416,11 +418,12 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_walk4 (updatePartials, whole op list per launch)"
                      if S <= 4 else "k_walk_generic", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": byt, "algorithmic_flops_per_launch": flo,
-                     "gflops": flo / (k_avg_ms * 1e-3) / 1e9, "avg_launch_ms": k_avg_ms,
+                     "algorithmic_bytes_per_step": byt, "algorithmic_flops_per_step": flo,
+                     "gflops": flo / (k_avg_ms * 1e-3) / 1e9, "partials_ms_per_step": k_avg_ms,
+                     "launches_per_step": k_n / args.steps,
                      "op_mix": ev.mix, "share_of_step": k_ms / dev_ms,
-                     "other_kernels_ms_per_step": {"transition_matrices": m_ms / max(m_n, 1),
-                                                   "root": r_ms / max(r_n, 1)}},
+                     "other_kernels_ms_per_step": {"transition_matrices": m_ms / args.steps,
+                                                   "root": r_ms / args.steps}},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "evals/s", "ms_per_step": 1e3 * e2e_s / args.steps,
                 "h2d_bytes_per_step": ev.h2d_bytes(S, C), "d2h_bytes_per_step": 8, "logL": float(last)},
         "gpu_launches": int(k_n + m_n + r_n),

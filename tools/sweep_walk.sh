@@ -1,19 +1,23 @@
 #!/bin/bash
 # Kernel-variant sweep for the 4-state walk (run on the GPU box): one bench line per setting.
+# columns: variant(0 global,1 stack) reorder block stackDepth phaseT(0=auto) R(patterns/thread)
 mkdir -p gpurun_out
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1   # builds the alignment cache
-for cfg in "0 1 128 12" "1 1 32 12" "1 1 64 12" "1 1 128 12" "1 1 256 12" "1 0 128 12"; do
+CFGS=${CFGS:-"0 1 128 12 0 1;0 1 128 12 0 2;0 1 128 12 0 4;1 1 128 12 0 1;1 1 128 12 0 2;1 1 128 12 0 4;0 1 64 12 0 2;0 1 256 12 0 2;0 1 128 12 32 2;0 1 128 12 32 4;1 1 64 12 32 2;0 1 128 12 16 4"}
+IFS=';' read -ra LIST <<< "$CFGS"
+for cfg in "${LIST[@]}"; do
   set -- $cfg
-  echo "variant=$1 reorder=$2 block=$3 depth=$4"
-  B200_WALK_VARIANT=$1 B200_REORDER=$2 B200_WALK_BLOCK=$3 B200_STACK_DEPTH=$4 \
-    python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>&1 | python -c "
+  echo "variant=$1 reorder=$2 block=$3 depth=$4 phaseT=$5 R=$6"
+  B200_WALK_VARIANT=$1 B200_REORDER=$2 B200_WALK_BLOCK=$3 B200_STACK_DEPTH=$4 B200_PHASE_T=$5 B200_WALK_R=$6 \
+    python bench.py --steps ${STEPS:-100} --warmup 5 --no-cpu-baseline $BENCH_ARGS 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
         d = json.loads(l)
-        print('  value %.1f evals/s  e2e %.1f  ms/step %.4f  walk %.4f ms  %.0f GB/s (frac %.3f)  %.1f GF/s  mat %.4f root %.4f logL %.6f' % (
-            d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['gflops'],
-            d['roofline']['other_kernels_ms_per_step']['transition_matrices'], d['roofline']['other_kernels_ms_per_step']['root'], d['logL']))
+        r = d['roofline']
+        print('  value %.1f evals/s  e2e %.1f  ms/step %.4f  partials %.4f ms/step (%d launches/step)  %.0f GB/s (frac %.3f)  %.1f GF/s  mat %.4f root %.4f logL %.6f' % (
+            d['value'], d['e2e']['value'], d['ms_per_step'], r['partials_ms_per_step'], r['launches_per_step'], r['achieved'], r['frac'], r['gflops'],
+            r['other_kernels_ms_per_step']['transition_matrices'], r['other_kernels_ms_per_step']['root'], d['logL']))
     else:
         sys.stdout.write(l)
 "
