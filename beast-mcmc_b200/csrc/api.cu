@@ -200,7 +200,8 @@ struct Plan {
     std::vector<int> phaseStart;     // index into subs; size = phases + 1
 };
 
-void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder, int T, Plan& plan) {
+void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder, int fixedT, int wantSubs, int minT,
+                Plan& plan) {
     const int n = (int)ops.size();
     auto single = [&]() {
         plan.order.resize(n);
@@ -228,6 +229,8 @@ void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder,
     plan.subs.clear(); plan.phaseStart.assign(1, 0);
     int remaining = n;
     while (remaining > 0) {
+        // per-phase subtree bound: enough subtrees to fill the machine, re-evaluated on what is left
+        const int T = fixedT > 0 ? fixedT : std::max(minT, (remaining + wantSubs - 1) / wantSubs);
         for (int k = 0; k < n; ++k) {
             if (!alive[k]) continue;
             const int a = (ch0[k] >= 0 && alive[ch0[k]]) ? ch0[k] : -1;
@@ -287,15 +290,11 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     const bool fourState = in->matCP > 0;
     Plan plan;
     {
-        int T = in->phaseT;
-        if (T <= 0) {
-            // enough (subtree x tile) walks to put ~32 warps on every SM, 4x oversubscribed for balance
-            const int cellsPerWarp = fourState ? (32 / in->matCP) * in->walkR : 1;
-            const int warpsPerSub = fourState ? (in->Ppad + cellsPerWarp - 1) / cellsPerWarp : std::max(1, in->Ppad / 4);
-            const int wantSubs = std::max(1, 4 * ((in->smCount * 32 + warpsPerSub - 1) / warpsPerSub));
-            T = std::max(8, (n + wantSubs - 1) / wantSubs);
-        }
-        planPhases(hops, in->nBuffers, in->reorder && !byPartition, T, plan);
+        // enough (subtree x tile) walks to put ~32 warps on every SM, 4x oversubscribed for balance
+        const int cellsPerWarp = fourState ? (32 / in->matCP) * in->walkR : 1;
+        const int warpsPerSub = fourState ? (in->Ppad + cellsPerWarp - 1) / cellsPerWarp : std::max(1, in->Ppad / 4);
+        const int wantSubs = std::max(1, in->phaseOversub * ((in->smCount * 32 + warpsPerSub - 1) / warpsPerSub));
+        planPhases(hops, in->nBuffers, in->reorder && !byPartition, in->phaseT, wantSubs, in->phaseTmin, plan);
     }
     const std::vector<int>& order = plan.order;
 
@@ -494,11 +493,13 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->partials.assign(in->nBuffers, nullptr);
     in->states8.assign(in->nBuffers, nullptr);
     in->states32.assign(in->nBuffers, nullptr);
-    in->walkBlock = envInt("B200_WALK_BLOCK", 128);
-    if (in->walkBlock < 32 || in->walkBlock > 256 || (in->walkBlock & 31)) in->walkBlock = 128;
-    in->walkVariant = envInt("B200_WALK_VARIANT", 1);
+    in->walkBlock = 128;
+    in->walkVariant = envInt("B200_WALK_VARIANT", 0);
     in->reorder = envInt("B200_REORDER", 1);
     in->phaseT = envInt("B200_PHASE_T", 0);
+    in->phaseTmin = std::max(1, envInt("B200_PHASE_TMIN", 4));
+    in->phaseOversub = std::max(1, envInt("B200_PHASE_OVERSUB", 3));
+    in->walkMinBlocks = envInt("B200_WALK_MINB", 5);
     in->walkR = envInt("B200_WALK_R", 2);
     if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4) in->walkR = 2;
     in->stackDepthMax = std::min(64, std::max(0, envInt("B200_STACK_DEPTH", 12)));

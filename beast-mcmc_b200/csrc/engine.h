@@ -99,11 +99,13 @@ struct Instance {
 
     // tuning knobs (environment overridable, see api.cu)
     size_t walkSmemConfigured = 0, genericSmemConfigured = 0;
-    int walkBlock = 64;
+    int walkBlock = 128;
     int walkVariant = 0;
     int reorder = 1;
     int stackDepthMax = 12;
+    int walkMinBlocks = 5;       // __launch_bounds__(128, n) variant of the 4-state walk (4, 5 or 6)
     int walkR = 2;               // patterns per thread in the 4-state walk (1, 2 or 4)
+    int phaseTmin = 4, phaseOversub = 4;
     int phaseT = 0;              // max ops per subtree walk (0 = automatic)
 };
 

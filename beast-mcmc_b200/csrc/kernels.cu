@@ -163,8 +163,55 @@ __device__ __forceinline__ void applyMat(const Mat4& M, const double (&x)[4], do
 // 128 B per child, more than the partials themselves, so each thread keeps its category's two
 // matrices in registers and re-uses them for R patterns (R = patterns per thread, strided by G so
 // that every load/store instruction still covers 8 consecutive patterns = 256 contiguous bytes).
-template <int CP, int R, bool STACK>
-__global__ void __launch_bounds__(256)
+// one child's contribution for the R patterns of this thread: y[r][i] (*)= sum_j P[i][j] x_r[j]
+template <int CP, int R, bool STACK, bool FIRST>
+__device__ __forceinline__ void childTerm(const WalkArgs& A, int child, int matIdx, int slot, int moff, size_t off0,
+                                          int p0, bool catValid, int pBegin, int pEnd, const double2* stackMem,
+                                          int nthreads, double (&y)[R][4]) {
+    constexpr int G = 32 / CP;
+    const int S = A.S;
+    const double* m = A.mats + (size_t)matIdx * (16 * CP) + moff;
+    if (child < 0) {
+        const uint8_t* t = A.states + (size_t)(-child - 1) * A.Ppad;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r * G;
+            const bool active = catValid && p < A.Ppad && p >= pBegin && p < pEnd;
+            const int s = active ? (int)__ldg(t + (p < A.Ppad ? p : 0)) : S;
+            double v[4];
+            if (s < S) ldg256_ro(m + 4 * CP * s, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = (i < S) ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[r][i] = FIRST ? v[i] : y[r][i] * v[i];
+        }
+    } else {
+        Mat4 M;
+        loadMat<CP>(m, M);
+        const double* xg = A.partials + (size_t)child * A.stride + off0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r * G;
+            const bool active = catValid && p < A.Ppad && p >= pBegin && p < pEnd;
+            double x[4], v[4];
+            if (STACK && slot != 0xFF) {
+                double2 lo = stackMem[((slot * R + r) * 2 + 0) * nthreads + threadIdx.x];
+                double2 hi = stackMem[((slot * R + r) * 2 + 1) * nthreads + threadIdx.x];
+                x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
+            } else if (active) {
+                ldg256(xg + (size_t)r * G * 4, x);
+            } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
+            applyMat(M, x, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[r][i] = FIRST ? v[i] : y[r][i] * v[i];
+        }
+    }
+}
+
+template <int CP, int R, bool STACK, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_walk4(const WalkArgs A) {
     constexpr int G = 32 / CP;
     extern __shared__ double2 stackMem[];
@@ -177,7 +224,6 @@ k_walk4(const WalkArgs A) {
     const size_t off0 = ((size_t)cc * A.Ppad + p0) * 4;
     const int moff = cc * 4;
     const int nthreads = blockDim.x;
-    const int S = A.S;
     const int2 range = __ldg(A.subs + blockIdx.y);
     const int last = range.y - 1;
 
@@ -185,73 +231,23 @@ k_walk4(const WalkArgs A) {
     for (int k = range.x; k <= last; ++k) {
         const Op4 nxt = loadOp(A.ops + min(k + 1, last));      // one record ahead, off the dependent chain
         const int s1 = cur.slots & 0xFF, s2 = (cur.slots >> 8) & 0xFF, sd = (cur.slots >> 16) & 0xFF;
-        const double* m1 = A.mats + (size_t)cur.m1 * (16 * CP) + moff;
-        const double* m2 = A.mats + (size_t)cur.m2 * (16 * CP) + moff;
-        Mat4 M1, M2;
-        if (cur.c1 >= 0) loadMat<CP>(m1, M1);
-        if (cur.c2 >= 0) loadMat<CP>(m2, M2);
-        const uint8_t* t1 = A.states + (size_t)(cur.c1 < 0 ? -cur.c1 - 1 : 0) * A.Ppad;
-        const uint8_t* t2 = A.states + (size_t)(cur.c2 < 0 ? -cur.c2 - 1 : 0) * A.Ppad;
-        const double* x1g = A.partials + (size_t)(cur.c1 >= 0 ? cur.c1 : 0) * A.stride + off0;
-        const double* x2g = A.partials + (size_t)(cur.c2 >= 0 ? cur.c2 : 0) * A.stride + off0;
+        double d[R][4];
+        childTerm<CP, R, STACK, true>(A, cur.c1, cur.m1, s1, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
+        childTerm<CP, R, STACK, false>(A, cur.c2, cur.m2, s2, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
         double* dg = A.partials + (size_t)cur.dest * A.stride + off0;
-
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int p = p0 + r * G;
             const bool active = catValid && p < A.Ppad && p >= cur.pBegin && p < cur.pEnd;
-            const int pc = p < A.Ppad ? p : 0;
-            double a[4], b[4], d[4];
-            // ---- child 1 --------------------------------------------------------------------
-            if (cur.c1 < 0) {
-                const int s = active ? (int)__ldg(t1 + pc) : S;
-                if (s < S) ldg256_ro(m1 + 4 * CP * s, a);
-                else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = (i < S) ? 1.0 : 0.0;
-                }
-            } else {
-                double x[4];
-                if (STACK && s1 != 0xFF) {
-                    double2 lo = stackMem[((s1 * R + r) * 2 + 0) * nthreads + threadIdx.x];
-                    double2 hi = stackMem[((s1 * R + r) * 2 + 1) * nthreads + threadIdx.x];
-                    x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
-                } else if (active) {
-                    ldg256(x1g + (size_t)r * G * 4, x);
-                } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
-                applyMat(M1, x, a);
-            }
-            // ---- child 2 --------------------------------------------------------------------
-            if (cur.c2 < 0) {
-                const int s = active ? (int)__ldg(t2 + pc) : S;
-                if (s < S) ldg256_ro(m2 + 4 * CP * s, b);
-                else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) b[i] = (i < S) ? 1.0 : 0.0;
-                }
-            } else {
-                double x[4];
-                if (STACK && s2 != 0xFF) {
-                    double2 lo = stackMem[((s2 * R + r) * 2 + 0) * nthreads + threadIdx.x];
-                    double2 hi = stackMem[((s2 * R + r) * 2 + 1) * nthreads + threadIdx.x];
-                    x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
-                } else if (active) {
-                    ldg256(x2g + (size_t)r * G * 4, x);
-                } else { x[0] = x[1] = x[2] = x[3] = 0.0; }
-                applyMat(M2, x, b);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = a[i] * b[i];
-
             // ---- rescaling (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE) -----
             if (cur.sw >= 0) {
-                double m = active ? fmax(fmax(d[0], d[1]), fmax(d[2], d[3])) : 0.0;
+                double m = active ? fmax(fmax(d[r][0], d[r][1]), fmax(d[r][2], d[r][3])) : 0.0;
 #pragma unroll
                 for (int sh = G; sh < 32; sh <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, sh));
                 if (m == 0.0) m = 1.0;
                 const double inv = 1.0 / m;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) d[i] *= inv;
+                for (int i = 0; i < 4; ++i) d[r][i] *= inv;
                 if (active && c == 0) {
                     const double lm = log(m);
                     A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
@@ -263,41 +259,42 @@ k_walk4(const WalkArgs A) {
                 if (A.logScalers) f = exp(f);
                 const double inv = 1.0 / f;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) d[i] *= inv;
+                for (int i = 0; i < 4; ++i) d[r][i] *= inv;
             }
-
-            if (active) stg256(dg + (size_t)r * G * 4, d);
+            if (active) stg256(dg + (size_t)r * G * 4, d[r]);
             if (STACK && sd != 0xFF) {
-                stackMem[((sd * R + r) * 2 + 0) * nthreads + threadIdx.x] = make_double2(d[0], d[1]);
-                stackMem[((sd * R + r) * 2 + 1) * nthreads + threadIdx.x] = make_double2(d[2], d[3]);
+                stackMem[((sd * R + r) * 2 + 0) * nthreads + threadIdx.x] = make_double2(d[r][0], d[r][1]);
+                stackMem[((sd * R + r) * 2 + 1) * nthreads + threadIdx.x] = make_double2(d[r][2], d[r][3]);
             }
         }
         cur = nxt;
     }
 }
 
+template <int CP, int R, bool STACK, int MINB>
+static cudaError_t launchWalk4K(Instance* in, const WalkArgs& A, dim3 grid, size_t smem) {
+    if (smem > 0 && smem > in->walkSmemConfigured) {
+        cudaError_t e = cudaFuncSetAttribute(k_walk4<CP, R, STACK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        in->walkSmemConfigured = smem;
+    }
+    k_walk4<CP, R, STACK, MINB><<<grid, 128, smem, in->stream>>>(A);
+    return cudaGetLastError();
+}
+
 template <int CP, int R>
 static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth) {
     constexpr int G = 32 / CP;
     const int warps = (in->Ppad + G * R - 1) / (G * R);
-    const int wpb = in->walkBlock / 32;
-    dim3 grid((warps + wpb - 1) / wpb, nSubs);
+    dim3 grid((warps + 3) / 4, nSubs);
     WalkArgs A;
     A.ops = dOps; A.subs = dSubs; A.partials = in->partialsBase; A.stride = in->partialsElems;
     A.states = in->states8Base; A.mats = in->dMat; A.scale = in->dScale;
     A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.logScalers = in->logScalers ? 1 : 0;
-    if (stackDepth > 0) {
-        size_t smem = (size_t)stackDepth * 32 * R * in->walkBlock;
-        if (smem > in->walkSmemConfigured) {
-            cudaError_t e = cudaFuncSetAttribute(k_walk4<CP, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            in->walkSmemConfigured = smem;
-        }
-        k_walk4<CP, R, true><<<grid, in->walkBlock, smem, in->stream>>>(A);
-    } else {
-        k_walk4<CP, R, false><<<grid, in->walkBlock, 0, in->stream>>>(A);
-    }
-    return cudaGetLastError();
+    if (stackDepth > 0) return launchWalk4K<CP, R, true, 4>(in, A, grid, (size_t)stackDepth * 32 * R * 128);
+    if (in->walkMinBlocks >= 6) return launchWalk4K<CP, R, false, 6>(in, A, grid, 0);
+    if (in->walkMinBlocks == 5) return launchWalk4K<CP, R, false, 5>(in, A, grid, 0);
+    return launchWalk4K<CP, R, false, 4>(in, A, grid, 0);
 }
 
 template <int CP>

@@ -1,14 +1,14 @@
 #!/bin/bash
 # Kernel-variant sweep for the 4-state walk (run on the GPU box): one bench line per setting.
-# columns: variant(0 global,1 stack) reorder block stackDepth phaseT(0=auto) R(patterns/thread)
+# columns: variant(0 global,1 stack) reorder minBlocks stackDepth phaseT(0=auto) R(patterns/thread) Tmin oversub
 mkdir -p gpurun_out
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1   # builds the alignment cache
-CFGS=${CFGS:-"0 1 128 12 0 1;0 1 128 12 0 2;0 1 128 12 0 4;1 1 128 12 0 1;1 1 128 12 0 2;1 1 128 12 0 4;0 1 64 12 0 2;0 1 256 12 0 2;0 1 128 12 32 2;0 1 128 12 32 4;1 1 64 12 32 2;0 1 128 12 16 4"}
+CFGS=${CFGS:-"0 1 4 12 0 2 4 4;0 1 5 12 0 2 4 4;0 1 6 12 0 2 4 4;0 1 4 12 0 4 4 4;0 1 5 12 0 4 4 4;0 1 5 12 0 1 4 4;0 1 5 12 0 2 1 4;0 1 5 12 0 2 2 4;0 1 5 12 0 2 8 4;0 1 5 12 0 2 4 2;0 1 5 12 0 2 4 8;0 1 5 12 0 2 4 16;1 1 4 12 0 2 4 4"}
 IFS=';' read -ra LIST <<< "$CFGS"
 for cfg in "${LIST[@]}"; do
   set -- $cfg
-  echo "variant=$1 reorder=$2 block=$3 depth=$4 phaseT=$5 R=$6"
-  B200_WALK_VARIANT=$1 B200_REORDER=$2 B200_WALK_BLOCK=$3 B200_STACK_DEPTH=$4 B200_PHASE_T=$5 B200_WALK_R=$6 \
+  echo "variant=$1 reorder=$2 minb=$3 depth=$4 phaseT=$5 R=$6 Tmin=$7 oversub=$8"
+  B200_WALK_VARIANT=$1 B200_REORDER=$2 B200_WALK_MINB=$3 B200_STACK_DEPTH=$4 B200_PHASE_T=$5 B200_WALK_R=$6 B200_PHASE_TMIN=$7 B200_PHASE_OVERSUB=$8 \
     python bench.py --steps ${STEPS:-100} --warmup 5 --no-cpu-baseline $BENCH_ARGS 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
