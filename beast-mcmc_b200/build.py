@@ -71,7 +71,7 @@ def build_oracle(force=False, verbose=False):
         return None
     out = os.path.join(ROOT, "oracle", "liboracle_cpu.so")
     if force or _stale(out, [src]):
-        _run(["gcc", "-O3", "-march=native", "-std=c11", "-fPIC", "-shared", "-pthread", "-o", out, src, "-lm"],
+        _run(["gcc", "-O3", "-march=native", "-std=gnu11", "-fPIC", "-shared", "-pthread", "-o", out, src, "-lm"],
              verbose)
     return out
 

@@ -32,7 +32,50 @@ typedef struct {
     double* freqs;       /* [S] */
     double* patternWeights;
     double* site;
+    /* persistent worker pool (threads-1 workers + the caller), two barriers per job */
+    pthread_t* workers;
+    pthread_barrier_t startBar, endBar;
+    int poolReady, quit, jobKind;
+    /* job arguments */
+    const int* jobOps; int jobNOps, jobCum;
+    int jobEigen; const int* jobProb; const double* jobLen; int jobCount;
 } OracleCpu;
+
+typedef struct { OracleCpu* o; int tid; } WorkerArg;
+static void run_job(OracleCpu* o, int tid);
+
+static void* worker_main(void* arg) {
+    WorkerArg* w = (WorkerArg*)arg;
+    OracleCpu* o = w->o;
+    const int tid = w->tid;
+    free(w);
+    for (;;) {
+        pthread_barrier_wait(&o->startBar);
+        if (o->quit) break;
+        run_job(o, tid);
+        pthread_barrier_wait(&o->endBar);
+    }
+    return NULL;
+}
+
+static void pool_run(OracleCpu* o, int kind) {
+    if (o->threads <= 1) { o->jobKind = kind; run_job(o, 0); return; }
+    if (!o->poolReady) {
+        pthread_barrier_init(&o->startBar, NULL, o->threads);
+        pthread_barrier_init(&o->endBar, NULL, o->threads);
+        o->workers = (pthread_t*)malloc(sizeof(pthread_t) * o->threads);
+        for (int t = 1; t < o->threads; ++t) {
+            WorkerArg* w = (WorkerArg*)malloc(sizeof(WorkerArg));
+            w->o = o; w->tid = t;
+            pthread_create(&o->workers[t], NULL, worker_main, w);
+        }
+        o->poolReady = 1;
+    }
+    o->jobKind = kind;
+    pthread_barrier_wait(&o->startBar);
+    run_job(o, 0);
+    pthread_barrier_wait(&o->endBar);
+}
 
 #define EXPORT __attribute__((visibility("default")))
 
@@ -58,6 +101,13 @@ EXPORT OracleCpu* oc_create(int tipCount, int nBuffers, int S, int P, int nEigen
 }
 
 EXPORT void oc_free(OracleCpu* o) {
+    if (o->poolReady) {
+        o->quit = 1;
+        pthread_barrier_wait(&o->startBar);
+        for (int t = 1; t < o->threads; ++t) pthread_join(o->workers[t], NULL);
+        pthread_barrier_destroy(&o->startBar); pthread_barrier_destroy(&o->endBar);
+        free(o->workers);
+    }
     for (int b = 0; b < o->nBuffers; ++b) { free(o->partials[b]); free(o->states[b]); }
     free(o->partials); free(o->states); free(o->eigen); free(o->matrices); free(o->scale); free(o->rates);
     free(o->weights); free(o->freqs); free(o->patternWeights); free(o->site); free(o);
@@ -90,21 +140,21 @@ EXPORT void oc_set_eigen(OracleCpu* o, int idx, const double* evec, const double
     memcpy(e + 2 * S * S, eval, sizeof(double) * S);
 }
 
-/* BaseSubstitutionModel.java:206-241 */
-EXPORT void oc_update_transition_matrices(OracleCpu* o, int eigenIdx, const int* probIdx, const double* lengths, int count) {
+/* BaseSubstitutionModel.java:206-241; branches [b0,b1) */
+static void matrices_range(OracleCpu* o, int b0, int b1) {
     const int S = o->S, C = o->C;
-    const double* evec = o->eigen + (size_t)eigenIdx * (2 * S * S + S);
+    const double* evec = o->eigen + (size_t)o->jobEigen * (2 * S * S + S);
     const double* ievc = evec + S * S;
     const double* eval = ievc + S * S;
     double* iexp = (double*)malloc(sizeof(double) * S * S);
-    for (int b = 0; b < count; ++b)
+    for (int b = b0; b < b1; ++b)
         for (int c = 0; c < C; ++c) {
-            const double d = lengths[b] * o->rates[c];
+            const double d = o->jobLen[b] * o->rates[c];
             for (int i = 0; i < S; ++i) {
                 const double t = exp(d * eval[i]);
                 for (int j = 0; j < S; ++j) iexp[i * S + j] = ievc[i * S + j] * t;
             }
-            double* m = o->matrices + ((size_t)probIdx[b] * C + c) * S * S;
+            double* m = o->matrices + ((size_t)o->jobProb[b] * C + c) * S * S;
             for (int i = 0; i < S; ++i)
                 for (int j = 0; j < S; ++j) {
                     double t = 0.0;
@@ -113,6 +163,11 @@ EXPORT void oc_update_transition_matrices(OracleCpu* o, int eigenIdx, const int*
                 }
         }
     free(iexp);
+}
+
+EXPORT void oc_update_transition_matrices(OracleCpu* o, int eigenIdx, const int* probIdx, const double* lengths, int count) {
+    o->jobEigen = eigenIdx; o->jobProb = probIdx; o->jobLen = lengths; o->jobCount = count;
+    pool_run(o, 1);
 }
 
 typedef struct { OracleCpu* o; const int* ops; int nOps, cum, p0, p1; } WalkJob;
@@ -205,21 +260,28 @@ EXPORT void oc_update_partials(OracleCpu* o, const int* ops, int nOps, int cum) 
         ensure(o, ops[7 * k]);
         free(o->states[ops[7 * k]]); o->states[ops[7 * k]] = NULL;
     }
-    int T = o->threads;
-    if (T > o->P) T = o->P;
-    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * T);
-    WalkJob* jobs = (WalkJob*)malloc(sizeof(WalkJob) * T);
-    const int div = o->P / T, rem = o->P % T;
-    int start = 0;
-    for (int t = 0; t < T; ++t) {
-        int n = div + (t < rem ? 1 : 0);
-        jobs[t] = (WalkJob){o, ops, nOps, cum, start, start + n};
-        start += n;
-        if (t > 0) pthread_create(&th[t], NULL, walk_block, &jobs[t]);
+    o->jobOps = ops; o->jobNOps = nOps; o->jobCum = cum;
+    pool_run(o, 0);
+}
+
+static void split(int n, int T, int tid, int* a, int* b) {
+    const int div = n / T, rem = n % T;
+    *a = tid * div + (tid < rem ? tid : rem);
+    *b = *a + div + (tid < rem ? 1 : 0);
+}
+
+static void run_job(OracleCpu* o, int tid) {
+    int a, b;
+    if (o->jobKind == 0) {
+        split(o->P, o->threads, tid, &a, &b);      /* contiguous pattern blocks (Patterns.java:142-169 rule) */
+        if (b > a) {
+            WalkJob w = {o, o->jobOps, o->jobNOps, o->jobCum, a, b};
+            walk_block(&w);
+        }
+    } else {
+        split(o->jobCount, o->threads, tid, &a, &b);
+        if (b > a) matrices_range(o, a, b);
     }
-    walk_block(&jobs[0]);
-    for (int t = 1; t < T; ++t) pthread_join(th[t], NULL);
-    free(th); free(jobs);
 }
 
 EXPORT void oc_reset_scale_factors(OracleCpu* o, int cum) { memset(o->scale + (size_t)cum * o->P, 0, sizeof(double) * o->P); }

@@ -1,0 +1,75 @@
+"""The JNI tier (libhmsbeagle-jni.so): exported symbol set and argument lists against the jar's
+native descriptors (tests/golden/beagle_jar_abi.json), and a JVM-less drive of the exported
+Java_beagle_BeagleJNIWrapper_* entry points through a fake JNIEnv."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+import helpers as H
+from beast_mcmc_b200 import build
+
+ROOT = H.ROOT
+ABI = json.load(open(os.path.join(ROOT, "tests", "golden", "beagle_jar_abi.json")))
+TYPE2DESC = {"jint": "I", "jlong": "J", "jdouble": "D", "jintArray": "[I", "jdoubleArray": "[D", "jobject": "L"}
+
+
+@pytest.fixture(scope="module")
+def jni():
+    build.build_engine()
+    lib = build.build_jni()
+    exe = os.path.join(ROOT, "tests", "jni_fake", "fake_jvm")
+    src = exe + ".cpp"
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", exe, src, "-ldl"], check=True)
+    return lib, exe
+
+
+def test_all_47_natives_exported(jni):
+    lib, _ = jni
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    want = {"Java_beagle_BeagleJNIWrapper_" + n["name"] for n in ABI["natives"]}
+    assert len(want) == 47
+    assert want <= exported, sorted(want - exported)
+
+
+def test_native_argument_lists_match_descriptors():
+    src = open(os.path.join(ROOT, "beast-mcmc_b200", "csrc", "jni_shim.cpp")).read()
+    defs = dict()
+    for m in re.finditer(r"NATIVE\((\w+), (\w+)\)\(([^)]*)\)", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        types = [a.strip().split()[0] for a in args.split(",")]
+        assert types[0] == "JNIEnv*" and types[1] == "jobject", name     # instance method of the singleton
+        defs[name] = (ret, types[2:])
+    for n in ABI["natives"]:
+        ret, types = defs[n["name"]]
+        params, rdesc = re.match(r"\((.*)\)(.*)", n["descriptor"]).groups()
+        params = re.sub(r"L[^;]+;", "L", params)
+        got = "".join(TYPE2DESC[t] for t in types)
+        assert got == params, (n["name"], got, params)
+        assert {"I": "jint"}.get(rdesc, "jstring" if "String" in rdesc else "jobjectArray") == ret, n["name"]
+
+
+def test_fake_jvm_info(jni):
+    lib, exe = jni
+    out = subprocess.run([exe, lib, "info"], capture_output=True, text=True, check=True).stdout
+    assert re.search(r"version (\d+)\.\d+\.\d+", out) and int(re.search(r"version (\d+)", out).group(1)) >= 4
+    assert "resource 0 name=CPU" in out
+
+
+@pytest.mark.gpu
+def test_fake_jvm_tiny_test(jni, tmp_path):
+    """BeagleFactory.main's tiny test through the JNI entry points: PAUP logL -1574.63623."""
+    lib, exe = jni
+    tree, pats, model, site, expected = H.tiny_case()
+    fx = tmp_path / "tiny.txt"
+    with open(fx, "w") as f:
+        f.write(f"3 {pats.patternCount}\n")
+        for t in range(3):
+            f.write(" ".join(str(int(s)) for s in pats.states[t]) + "\n")
+    out = subprocess.run([exe, lib, "tiny", str(fx)], capture_output=True, text=True, check=True).stdout
+    assert f"logL {expected:.5f} rc 0" in out, out
+    assert "impl=B200-CUDA-Double" in out
