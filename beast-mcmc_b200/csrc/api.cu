@@ -291,8 +291,9 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     Plan plan;
     {
         // enough (subtree x tile) walks to put ~32 warps on every SM, 4x oversubscribed for balance
-        const int cellsPerWarp = fourState ? (32 / in->matCP) * in->walkR : 1;
-        const int warpsPerSub = fourState ? (in->Ppad + cellsPerWarp - 1) / cellsPerWarp : std::max(1, in->Ppad / 4);
+        // patterns one warp owns: FMA kernel (32/CP)*R, tensor kernel 8*R (all categories)
+        const int patsPerWarp = !fourState ? 4 : (in->walkVariant == 2 ? 8 * std::min(in->walkR, 2) : (32 / in->matCP) * in->walkR);
+        const int warpsPerSub = std::max(1, (in->Ppad + patsPerWarp - 1) / patsPerWarp);
         const int wantSubs = std::max(1, in->phaseOversub * ((in->smCount * 32 + warpsPerSub - 1) / warpsPerSub));
         planPhases(hops, in->nBuffers, in->reorder && !byPartition, in->phaseT, wantSubs, in->phaseTmin, plan);
     }
@@ -301,7 +302,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     // ---- stack slots (4-state path only): one backward pass finds, for every produced value, the
     // position of its LAST reader inside this list (before the buffer is re-written); the forward
     // pass then parks results in slots and frees each slot at that last read.
-    const int maxDepth = (fourState && !byPartition && in->walkVariant >= 1) ? in->stackDepthMax : 0;
+    const int maxDepth = (fourState && !byPartition && in->walkVariant == 1) ? in->stackDepthMax : 0;
     std::vector<int> lastReadOfProd(maxDepth > 0 ? n : 0, -1);
     std::vector<int> subOfPos(n, 0);
     for (int sIdx = 0; sIdx < (int)plan.subs.size(); ++sIdx)
@@ -484,7 +485,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
         int cp = 1;
         while (cp < in->C) cp <<= 1;
         in->matCP = cp;
-        in->matStride = (size_t)16 * cp;
+        in->matStride = (size_t)16 * cp + 32 * (size_t)in->C;     // [j][CP][i] + M[c][i][j] + MT[c][j][i]
     } else {
         in->matCP = 0;
         in->matStride = (size_t)in->C * in->Sp * in->Sp;
@@ -822,7 +823,14 @@ int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMat
     for (int c = 0; c < in->C; ++c)
         for (int i = 0; i < in->S; ++i)
             for (int j = 0; j < in->S; ++j)
-                t[matIndex(in, c, i, j)] = inMatrix[((size_t)c * in->S + i) * in->S + j];
+            {
+                const double v = inMatrix[((size_t)c * in->S + i) * in->S + j];
+                t[matIndex(in, c, i, j)] = v;
+                if (in->matCP) {
+                    t[16 * in->matCP + (size_t)c * 16 + i * 4 + j] = v;
+                    t[16 * in->matCP + (size_t)in->C * 16 + (size_t)c * 16 + j * 4 + i] = v;
+                }
+            }
     CUDA_OK(cudaMemcpyAsync(in->dMat + matrixIndex * n, t.data(), sizeof(double) * n, cudaMemcpyHostToDevice, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
     return BEAGLE_SUCCESS;

@@ -90,6 +90,12 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
             acc = fabs(acc);
         }
         out[(size_t)j * rowStride + i] = acc;
+        if (matCP) {
+            // tensor-core path copies after the [j][CP][i] block: M[c][i][j] (B fragments) and MT[c][j][i] (tip columns)
+            double* mm = matBase + (size_t)probIdx[b] * matStride + 16 * matCP;
+            mm[(size_t)c * 16 + i * 4 + j] = acc;
+            mm[(size_t)C * 16 + (size_t)c * 16 + j * 4 + i] = acc;
+        }
     }
 }
 
@@ -127,6 +133,8 @@ struct WalkArgs {
     const double* mats;        // [matrix][4][CP][4]
     double* scale;             // [buffer][Ppad]
     int S, C, Ppad, logScalers;
+    size_t matStride;          // elements per matrix buffer
+    int matMmaOffset;          // offset of the [c][i][j] + [c][j][i] copies inside a matrix buffer
 };
 
 __device__ __forceinline__ Op4 loadOp(const Op4* p) {
@@ -170,7 +178,7 @@ __device__ __forceinline__ void childTerm(const WalkArgs& A, int child, int matI
                                           int nthreads, double (&y)[R][4]) {
     constexpr int G = 32 / CP;
     const int S = A.S;
-    const double* m = A.mats + (size_t)matIdx * (16 * CP) + moff;
+    const double* m = A.mats + (size_t)matIdx * A.matStride + moff;
     if (child < 0) {
         const uint8_t* t = A.states + (size_t)(-child - 1) * A.Ppad;
 #pragma unroll
@@ -291,10 +299,169 @@ static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int2* dSubs
     A.ops = dOps; A.subs = dSubs; A.partials = in->partialsBase; A.stride = in->partialsElems;
     A.states = in->states8Base; A.mats = in->dMat; A.scale = in->dScale;
     A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.logScalers = in->logScalers ? 1 : 0;
+    A.matStride = in->matStride; A.matMmaOffset = 16 * in->matCP;
     if (stackDepth > 0) return launchWalk4K<CP, R, true, 4>(in, A, grid, (size_t)stackDepth * 32 * R * 128);
     if (in->walkMinBlocks >= 6) return launchWalk4K<CP, R, false, 6>(in, A, grid, 0);
     if (in->walkMinBlocks == 5) return launchWalk4K<CP, R, false, 5>(in, A, grid, 0);
     return launchWalk4K<CP, R, false, 4>(in, A, grid, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4-state walk on the FP64 tensor pipe (DMMA m8n8k4)
+// ---------------------------------------------------------------------------------------------
+// D[p][i] = sum_j X[p][j] * P[i][j]  as one mma.sync.m8n8k4.f64 per (8 patterns, category, child):
+//   A fragment = child partials  [8 patterns][4 states]   lane (g,t) <- X[p0+g][t]     (256 contiguous bytes / warp)
+//   B fragment = transition rows [4 (j)][8 (i)]            lane (g,t) <- P[g][t], 0 for g >= 4 (128 contiguous bytes)
+//   D fragment                    [8 patterns][8 (i)]      lane (g,t) -> i = 2t,2t+1 of pattern g (valid for t < 2)
+// tcgen05 has no fp64 kind, so the fp64 tensor path on sm_100a is mma.sync (SASS DMMA.8x8x4).
+// Compared with the FMA kernel the matrix reaches the register file ONCE per warp (8 B/lane) instead of
+// once per thread (128 B/lane), which was what saturated the LSU->RF path.
+// Warp = all C categories x R tiles of 8 patterns; results stay in registers until the per-pattern
+// maximum over categories is known, so the rescale is fused.
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+template <int CMAX, int R>
+__global__ void __launch_bounds__(128)
+k_walk4m(const WalkArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int pBase = warp * (8 * R) + g;                  // pattern of tile r: pBase + 8 r
+    const int S = A.S, C = A.C;
+    const size_t mstride = A.matStride;
+    const int2 range = __ldg(A.subs + blockIdx.y);
+    const int last = range.y - 1;
+    const size_t catStride = (size_t)A.Ppad * 4;
+
+    Op4 cur = loadOp(A.ops + range.x);
+    for (int k = range.x; k <= last; ++k) {
+        const Op4 nxt = loadOp(A.ops + min(k + 1, last));
+        double y[CMAX][R][2];
+        bool act[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = pBase + 8 * r;
+            act[r] = p < A.Ppad && p >= cur.pBegin && p < cur.pEnd;
+        }
+#pragma unroll
+        for (int child = 0; child < 2; ++child) {
+            const int cb = child == 0 ? cur.c1 : cur.c2;
+            const double* mm = A.mats + (size_t)(child == 0 ? cur.m1 : cur.m2) * mstride + A.matMmaOffset;
+            if (cb >= 0) {
+                const double* x = A.partials + (size_t)cb * A.stride + (size_t)pBase * 4 + t;
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) {
+                    if (c < C) {
+                        const double b = (g < 4) ? __ldg(mm + c * 16 + g * 4 + t) : 0.0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            double a = 0.0, d0, d1;
+                            if (act[r]) asm volatile("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(x + c * catStride + (size_t)r * 32) : "memory");
+                            dmma884(d0, d1, a, b);
+                            if (child == 0) { y[c][r][0] = d0; y[c][r][1] = d1; }
+                            else { y[c][r][0] *= d0; y[c][r][1] *= d1; }
+                        }
+                    }
+                }
+            } else {
+                const uint8_t* st = A.states + (size_t)(-cb - 1) * A.Ppad;
+                const double* mt = mm + (size_t)C * 16;              // MT[c][j][i]
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int p = pBase + 8 * r;
+                    const int s = act[r] ? (int)__ldg(st + p) : S;
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) {
+                        if (c < C) {
+                            double v0 = (2 * t < S) ? 1.0 : 0.0, v1 = (2 * t + 1 < S) ? 1.0 : 0.0;
+                            if (s < S && t < 2) {
+                                const double2 col = __ldg(reinterpret_cast<const double2*>(mt + c * 16 + s * 4 + 2 * t));
+                                v0 = col.x; v1 = col.y;
+                            }
+                            if (t >= 2) { v0 = 0.0; v1 = 0.0; }
+                            if (child == 0) { y[c][r][0] = v0; y[c][r][1] = v1; }
+                            else { y[c][r][0] *= v0; y[c][r][1] *= v1; }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- fused rescale (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE) ---------
+        if (cur.sw >= 0 || cur.sr >= 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int p = pBase + 8 * r;
+                double f;
+                if (cur.sw >= 0) {
+                    double m = 0.0;
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) if (c < C) m = fmax(m, fmax(y[c][r][0], y[c][r][1]));
+                    if (!act[r] || t >= 2) m = 0.0;
+                    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                    if (m == 0.0) m = 1.0;
+                    f = m;
+                    if (act[r] && t == 0) {
+                        const double lm = log(m);
+                        A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
+                        if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
+                    }
+                } else {
+                    f = act[r] ? A.scale[(size_t)cur.sr * A.Ppad + p] : 1.0;
+                    if (A.logScalers) f = exp(f);
+                }
+                const double inv = 1.0 / f;
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) if (c < C) { y[c][r][0] *= inv; y[c][r][1] *= inv; }
+            }
+            __syncwarp();
+        }
+        // ---- store: lanes t < 2 own states 2t, 2t+1 (16 B) of pattern g ---------------------------
+        {
+            double* dst = A.partials + (size_t)cur.dest * A.stride + (size_t)pBase * 4 + 2 * t;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                if (c < C) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (act[r] && t < 2)
+                            asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(dst + c * catStride + (size_t)r * 32),
+                                         "d"(y[c][r][0]), "d"(y[c][r][1]) : "memory");
+                    }
+                }
+            }
+        }
+        __syncwarp();          // the next op may read (other lanes of this warp) what was just stored
+        cur = nxt;
+    }
+}
+
+template <int CMAX, int R>
+static cudaError_t launchWalk4M(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs) {
+    const int warps = (in->Ppad + 8 * R - 1) / (8 * R);
+    dim3 grid((warps + 3) / 4, nSubs);
+    WalkArgs A;
+    A.ops = dOps; A.subs = dSubs; A.partials = in->partialsBase; A.stride = in->partialsElems;
+    A.states = in->states8Base; A.mats = in->dMat; A.scale = in->dScale;
+    A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.logScalers = in->logScalers ? 1 : 0;
+    A.matStride = in->matStride; A.matMmaOffset = 16 * in->matCP;
+    k_walk4m<CMAX, R><<<grid, 128, 0, in->stream>>>(A);
+    return cudaGetLastError();
+}
+
+static cudaError_t launchWalk4Mma(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs) {
+    const bool r2 = in->walkR >= 2;
+    switch (in->matCP) {
+        case 1: return r2 ? launchWalk4M<1, 2>(in, dOps, dSubs, nSubs) : launchWalk4M<1, 1>(in, dOps, dSubs, nSubs);
+        case 2: return r2 ? launchWalk4M<2, 2>(in, dOps, dSubs, nSubs) : launchWalk4M<2, 1>(in, dOps, dSubs, nSubs);
+        case 4: return r2 ? launchWalk4M<4, 2>(in, dOps, dSubs, nSubs) : launchWalk4M<4, 1>(in, dOps, dSubs, nSubs);
+        case 8: return r2 ? launchWalk4M<8, 2>(in, dOps, dSubs, nSubs) : launchWalk4M<8, 1>(in, dOps, dSubs, nSubs);
+        case 16: return launchWalk4M<16, 1>(in, dOps, dSubs, nSubs);
+        default: return launchWalk4M<32, 1>(in, dOps, dSubs, nSubs);
+    }
 }
 
 template <int CP>
@@ -308,6 +475,7 @@ static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int2* dSubs
 
 cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth) {
     if (nSubs <= 0) return cudaSuccess;
+    if (in->walkVariant == 2) return launchWalk4Mma(in, dOps, dSubs, nSubs);
     switch (in->matCP) {
         case 1: return launchWalk4T<1>(in, dOps, dSubs, nSubs, stackDepth);
         case 2: return launchWalk4T<2>(in, dOps, dSubs, nSubs, stackDepth);
