@@ -292,9 +292,10 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     {
         // enough (subtree x tile) walks to put ~32 warps on every SM, 4x oversubscribed for balance
         // patterns one warp owns: FMA kernel (32/CP)*R, tensor kernel 8*R (all categories)
-        const int patsPerWarp = !fourState ? 4 : (in->walkVariant == 2 ? 8 * std::min(in->walkR, 2) : (32 / in->matCP) * in->walkR);
+        const int patsPerWarp = !fourState ? 16 : (in->walkVariant == 2 ? 8 * std::min(in->walkR, 2) : (32 / in->matCP) * in->walkR);
         const int warpsPerSub = std::max(1, (in->Ppad + patsPerWarp - 1) / patsPerWarp);
-        const int wantSubs = std::max(1, in->phaseOversub * ((in->smCount * 32 + warpsPerSub - 1) / warpsPerSub));
+        const int warpsPerSM = fourState ? 32 : 12;      // resident warps the kernel family can hold per SM
+        const int wantSubs = std::max(1, in->phaseOversub * ((in->smCount * warpsPerSM + warpsPerSub - 1) / warpsPerSub));
         planPhases(hops, in->nBuffers, in->reorder && !byPartition, in->phaseT, wantSubs, in->phaseTmin, plan);
     }
     const std::vector<int>& order = plan.order;
@@ -465,7 +466,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->tipCount = tipCount; in->nPartials = partialsBufferCount; in->nCompact = compactBufferCount;
     in->S = stateCount; in->P = patternCount; in->nEigen = eigenBufferCount; in->nMatrices = matrixBufferCount;
     in->C = categoryCount; in->nScale = scaleBufferCount;
-    in->Sp = stateCount <= 4 ? 4 : ((stateCount + 3) / 4) * 4;
+    in->Sp = stateCount <= 4 ? 4 : ((stateCount + 7) / 8) * 8;      // multiples of the 8x8x4 DMMA tile
     in->Ppad = ((patternCount + 31) / 32) * 32;
     in->nBuffers = partialsBufferCount + compactBufferCount;
     in->nSets = std::max(1, eigenBufferCount);
@@ -488,7 +489,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
         in->matStride = (size_t)16 * cp + 32 * (size_t)in->C;     // [j][CP][i] + M[c][i][j] + MT[c][j][i]
     } else {
         in->matCP = 0;
-        in->matStride = (size_t)in->C * in->Sp * in->Sp;
+        in->matStride = 2 * (size_t)in->C * in->Sp * in->Sp;     // MT[c][j][i] then M[c][i][j] (tensor-path B operand)
     }
     in->slotOf.assign(in->nBuffers, -1);
     in->partials.assign(in->nBuffers, nullptr);
@@ -501,6 +502,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->phaseTmin = std::max(1, envInt("B200_PHASE_TMIN", 4));
     in->phaseOversub = std::max(1, envInt("B200_PHASE_OVERSUB", 3));
     in->walkMinBlocks = envInt("B200_WALK_MINB", 5);
+    in->genericMma = envInt("B200_GENERIC_MMA", 1);
     in->walkR = envInt("B200_WALK_R", 2);
     if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4) in->walkR = 2;
     in->stackDepthMax = std::min(64, std::max(0, envInt("B200_STACK_DEPTH", 12)));
@@ -829,6 +831,8 @@ int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMat
                 if (in->matCP) {
                     t[16 * in->matCP + (size_t)c * 16 + i * 4 + j] = v;
                     t[16 * in->matCP + (size_t)in->C * 16 + (size_t)c * 16 + j * 4 + i] = v;
+                } else {
+                    t[(size_t)in->C * in->Sp * in->Sp + ((size_t)c * in->Sp + i) * in->Sp + j] = v;
                 }
             }
     CUDA_OK(cudaMemcpyAsync(in->dMat + matrixIndex * n, t.data(), sizeof(double) * n, cudaMemcpyHostToDevice, in->stream));

@@ -98,12 +98,13 @@ struct Instance {
     long timedLaunches[T_CLASSES] = {0, 0, 0};
 
     // tuning knobs (environment overridable, see api.cu)
-    size_t walkSmemConfigured = 0, genericSmemConfigured = 0;
+    size_t walkSmemConfigured = 0, genericSmemConfigured = 0, mmaSmemConfigured = 0;
     int walkBlock = 128;
     int walkVariant = 0;
     int reorder = 1;
     int stackDepthMax = 12;
     int walkMinBlocks = 5;       // __launch_bounds__(128, n) variant of the 4-state walk (4, 5 or 6)
+    int genericMma = 1;          // S > 4: 1 = fp64 tensor-core block walk, 0 = FMA block walk
     int walkR = 2;               // patterns per thread in the 4-state walk (1, 2 or 4)
     int phaseTmin = 4, phaseOversub = 4;
     int phaseT = 0;              // max ops per subtree walk (0 = automatic)

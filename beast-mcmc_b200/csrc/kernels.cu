@@ -90,7 +90,10 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
             acc = fabs(acc);
         }
         out[(size_t)j * rowStride + i] = acc;
-        if (matCP) {
+        if (!matCP) {
+            // generic layout: second half of the buffer holds the row-major M[c][i][j] (tensor-path B operand)
+            matBase[(size_t)probIdx[b] * matStride + (size_t)C * Sp * Sp + ((size_t)c * Sp + i) * Sp + j] = acc;
+        } else {
             // tensor-core path copies after the [j][CP][i] block: M[c][i][j] (B fragments) and MT[c][j][i] (tip columns)
             double* mm = matBase + (size_t)probIdx[b] * matStride + 16 * matCP;
             mm[(size_t)c * 16 + i * 4 + j] = acc;
@@ -587,8 +590,184 @@ k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// generic-state block walk on the FP64 tensor pipe (DMMA m8n8k4): amino-acid (20) and codon (61) models
+// ---------------------------------------------------------------------------------------------
+// Per (op, category) the contraction D[p][i] = sum_j X[p][j] P[i][j] is a (patterns x Sp) * (Sp x Sp)
+// GEMM: A fragments come straight from the child partials in global memory (each element is read
+// exactly once per op, so there is nothing to stage), B fragments from the row-major matrix staged in
+// shared memory with a (Sp+4)-double row stride (conflict-free for the 8x4 fragment shape), and the
+// 16 x Sp accumulator tile of each warp lives in registers.  Block = 4 warps x 16 patterns.
+__device__ __forceinline__ void dmma884acc(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128)
+k_walk_mma(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int S, int C, int Ppad, int logScalers) {
+    constexpr int Sp = 8 * NT;
+    constexpr int LD = Sp + 4;                       // shared-memory row stride (doubles)
+    extern __shared__ double smm[];
+    double* P1 = smm;
+    double* P2 = smm + Sp * LD;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int pw = blockIdx.x * 64 + w * 16;         // first pattern of this warp's 16-row tile
+    const int2 range = subs[blockIdx.y];
+    const size_t mRow = (size_t)C * Sp * Sp;         // offset of the row-major copies in a matrix buffer
+
+    for (int k = range.x; k < range.y; ++k) {
+        const DevOp op = ops[k];
+        bool act[2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int p = pw + 8 * m + g;
+            act[m] = p < Ppad && p >= op.pBegin && p < op.pEnd;
+        }
+        double rowMax[2] = {0.0, 0.0};
+        for (int c = 0; c < C; ++c) {
+            __syncthreads();
+            {   // stage both row-major matrices: global [i][j] (stride Sp) -> shared [i][j] (stride LD)
+                const double* g1 = op.m1 + mRow + (size_t)c * Sp * Sp;
+                const double* g2 = op.m2 + mRow + (size_t)c * Sp * Sp;
+                for (int q = tid; q < Sp * Sp / 2; q += 128) {
+                    const int i = (2 * q) / Sp, j = (2 * q) % Sp;
+                    const double2 v1 = __ldg(reinterpret_cast<const double2*>(g1) + q);
+                    const double2 v2 = __ldg(reinterpret_cast<const double2*>(g2) + q);
+                    *reinterpret_cast<double2*>(P1 + i * LD + j) = v1;
+                    *reinterpret_cast<double2*>(P2 + i * LD + j) = v2;
+                }
+            }
+            __syncthreads();
+            double acc[2][NT][2];
+#pragma unroll
+            for (int child = 0; child < 2; ++child) {
+                const double* xg = child == 0 ? op.c1 : op.c2;
+                const double* Ps = child == 0 ? P1 : P2;
+                double cur[2][NT][2];
+                if (xg != nullptr) {
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) { cur[m][n][0] = 0.0; cur[m][n][1] = 0.0; }
+                    const double* xrow0 = xg + ((size_t)c * Ppad + (pw + g)) * Sp + t;
+                    const double* xrow1 = xrow0 + (size_t)8 * Sp;
+                    const double* brow = Ps + g * LD + t;
+#pragma unroll 4
+                    for (int kc = 0; kc < Sp / 4; ++kc) {
+                        double a0 = 0.0, a1 = 0.0;
+                        if (act[0]) a0 = xrow0[4 * kc];
+                        if (act[1]) a1 = xrow1[4 * kc];
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) {
+                            const double b = brow[n * 8 * LD + 4 * kc];
+                            dmma884acc(cur[0][n][0], cur[0][n][1], a0, b);
+                            dmma884acc(cur[1][n][0], cur[1][n][1], a1, b);
+                        }
+                    }
+                } else {
+                    const int* st = static_cast<const int*>(child == 0 ? op.s1 : op.s2);
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const int p = pw + 8 * m + g;
+                        const int s = act[m] ? st[p] : S;
+#pragma unroll
+                        for (int n = 0; n < NT; ++n)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int i = 8 * n + 2 * t + e;
+                                cur[m][n][e] = (s < S) ? Ps[i * LD + s] : ((i < S) ? 1.0 : 0.0);
+                            }
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            acc[m][n][e] = child == 0 ? cur[m][n][e] : acc[m][n][e] * cur[m][n][e];
+            }
+            // store the (unscaled) tile: lane (g,t) owns states 8n+2t, 8n+2t+1 of rows g and g+8
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (!act[m]) continue;
+                double* drow = op.dest + ((size_t)c * Ppad + (pw + 8 * m + g)) * Sp + 2 * t;
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    *reinterpret_cast<double2*>(drow + 8 * n) = make_double2(acc[m][n][0], acc[m][n][1]);
+                    rowMax[m] = fmax(rowMax[m], fmax(acc[m][n][0], acc[m][n][1]));
+                }
+            }
+        }
+        if (op.scaleWrite != nullptr || op.scaleRead != nullptr) {
+            // per-pattern factor (max over categories and states), then one more pass over what this
+            // warp just wrote (same lanes re-read their own stores)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int p = pw + 8 * m + g;
+                double f;
+                if (op.scaleWrite != nullptr) {
+                    double mx = act[m] ? rowMax[m] : 0.0;
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    if (mx == 0.0) mx = 1.0;
+                    f = mx;
+                    if (act[m] && t == 0) {
+                        const double lm = log(mx);
+                        op.scaleWrite[p] = logScalers ? lm : mx;
+                        if (op.cumScale) op.cumScale[p] += lm;
+                    }
+                } else {
+                    f = act[m] ? op.scaleRead[p] : 1.0;
+                    if (logScalers) f = exp(f);
+                }
+                if (act[m]) {
+                    const double inv = 1.0 / f;
+                    for (int c = 0; c < C; ++c) {
+                        double* drow = op.dest + ((size_t)c * Ppad + p) * Sp + 2 * t;
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) {
+                            double2 v = *reinterpret_cast<double2*>(drow + 8 * n);
+                            v.x *= inv; v.y *= inv;
+                            *reinterpret_cast<double2*>(drow + 8 * n) = v;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();      // children of the next op may have been written by other warps? no: rows are warp-private,
+                              // but the shared matrices are about to be overwritten
+    }
+}
+
+template <int NT>
+static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int2* dSubs, int nSubs) {
+    constexpr int Sp = 8 * NT;
+    const size_t smem = 2 * (size_t)Sp * (Sp + 4) * sizeof(double);
+    if (smem > in->mmaSmemConfigured) {
+        cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        in->mmaSmemConfigured = smem;
+    }
+    dim3 grid((in->Ppad + 63) / 64, nSubs);
+    k_walk_mma<NT><<<grid, 128, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
+    return cudaGetLastError();
+}
+
 cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int2* dSubs, int nSubs) {
     if (nSubs <= 0) return cudaSuccess;
+    if (in->genericMma) {
+        switch (in->Sp / 8) {
+            case 1: return launchWalkMmaT<1>(in, dOps, dSubs, nSubs);
+            case 2: return launchWalkMmaT<2>(in, dOps, dSubs, nSubs);
+            case 3: return launchWalkMmaT<3>(in, dOps, dSubs, nSubs);
+            case 4: return launchWalkMmaT<4>(in, dOps, dSubs, nSubs);
+            case 8: return launchWalkMmaT<8>(in, dOps, dSubs, nSubs);
+            default: break;      // other state counts: FMA block walk below
+        }
+    }
     const int Sp = in->Sp;
     const size_t budget = in->maxSmemOptin > 16384 ? in->maxSmemOptin - 2048 : 46000;
     int stage = (2 * (size_t)Sp * Sp * 8 + 2 * 8 * (size_t)Sp * 8 + 64 <= budget) ? 1 : 0;
