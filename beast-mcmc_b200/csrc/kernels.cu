@@ -37,6 +37,13 @@ __device__ __forceinline__ void stg256(double* p, const double (&v)[4]) {
                  :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
+// fp64 tensor-core primitive (SASS DMMA.8x8x4): D(8x8) += A(8x4) * B(4x8); lane (g = lane/4, t = lane%4)
+// holds A[g][t], B[t][g] and D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void dmma884acc(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // ---------------------------------------------------------------------------------------------
 // transition matrices
 // ---------------------------------------------------------------------------------------------
@@ -102,9 +109,91 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
     }
 }
 
+// Tensor-core variant for real eigen systems with S > 4: one block per (branch, category) computes
+// P = Evec * (diag(exp(lambda r t)) * Ievc) as an Sp x Sp x Sp DMMA product.  Shared memory holds
+// A = Evec [i][k] and Bt[j][k] = exp(.)_k * Ievc[k][j], both with the conflict-free (Sp+4) row stride.
+template <int NT>
+__global__ void __launch_bounds__(128)
+k_transition_mma(const double* __restrict__ eigenBase, size_t eigenStride, int S, int C,
+                 const double* __restrict__ ratesBase, const int* __restrict__ probIdx,
+                 const int* __restrict__ eigenIdx, const int* __restrict__ rateSet,
+                 const double* __restrict__ lengths, double* __restrict__ matBase, size_t matStride) {
+    constexpr int Sp = 8 * NT;
+    constexpr int LD = Sp + 4;
+    extern __shared__ double smt[];
+    double* As = smt;                 // Evec[i][k]
+    double* Bt = smt + Sp * LD;       // Bt[j][k]
+    double* ex = Bt + Sp * LD;        // exp(d * lambda_k)
+    const int b = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    const double* E = eigenBase + (size_t)eigenIdx[b] * eigenStride;
+    const double* evec = E;
+    const double* ievc = E + (size_t)S * S;
+    const double* eval = E + 2 * (size_t)S * S;
+    const double d = lengths[b] * ratesBase[(size_t)rateSet[b] * C + c];
+    for (int k = tid; k < Sp; k += 128) ex[k] = k < S ? exp(d * eval[k]) : 0.0;
+    __syncthreads();
+    for (int q = tid; q < Sp * Sp; q += 128) {
+        const int r = q / Sp, col = q % Sp;
+        As[r * LD + col] = (r < S && col < S) ? evec[(size_t)r * S + col] : 0.0;                       // [i][k]
+        // q walks Ievc row-major ([k][j]) so the global read is coalesced; the shared write is the transpose
+        Bt[col * LD + r] = (r < S && col < S) ? ievc[(size_t)r * S + col] * ex[r] : 0.0;               // Bt[j][k]
+    }
+    __syncthreads();
+    const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    double* outT = matBase + (size_t)probIdx[b] * matStride + (size_t)c * Sp * Sp;                     // MT[j][i]
+    double* outR = matBase + (size_t)probIdx[b] * matStride + (size_t)C * Sp * Sp + (size_t)c * Sp * Sp;  // M[i][j]
+    for (int mt = w; mt < NT; mt += 4) {             // 8-row tiles of the output
+        double acc[NT][2];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+        const double* arow = As + (8 * mt + g) * LD + t;
+        const double* brow = Bt + g * LD + t;
+#pragma unroll 4
+        for (int kc = 0; kc < Sp / 4; ++kc) {
+            const double a = arow[4 * kc];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) dmma884acc(acc[n][0], acc[n][1], a, brow[n * 8 * LD + 4 * kc]);
+        }
+        const int i = 8 * mt + g;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const int j = 8 * n + 2 * t;
+            const double v0 = fabs(acc[n][0]), v1 = fabs(acc[n][1]);
+            *reinterpret_cast<double2*>(outR + (size_t)i * Sp + j) = make_double2(v0, v1);
+            outT[(size_t)j * Sp + i] = v0;
+            outT[(size_t)(j + 1) * Sp + i] = v1;
+        }
+    }
+}
+
+template <int NT>
+static cudaError_t launchTransitionMmaT(Instance* in, const int* dProbIdx, const int* dEigenIdx, const int* dRateSet,
+                                        const double* dLengths, int count) {
+    constexpr int Sp = 8 * NT;
+    const size_t smem = (2 * (size_t)Sp * (Sp + 4) + Sp) * sizeof(double);
+    static_assert(Sp <= 64, "shared-memory budget");
+    cudaError_t e = cudaFuncSetAttribute(k_transition_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(count, in->C);
+    k_transition_mma<NT><<<grid, 128, smem, in->stream>>>(in->dEigen, 2 * (size_t)in->S * in->S + 2 * in->S, in->S, in->C,
+                                                          in->dRates, dProbIdx, dEigenIdx, dRateSet, dLengths, in->dMat,
+                                                          in->matStride);
+    return cudaGetLastError();
+}
+
 cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const int* dEigenIdx,
                                      const int* dRateSet, const double* dLengths, int count) {
     if (count <= 0) return cudaSuccess;
+    if (in->genericMma && in->matCP == 0 && !in->complexEigen) {
+        switch (in->Sp / 8) {
+            case 1: return launchTransitionMmaT<1>(in, dProbIdx, dEigenIdx, dRateSet, dLengths, count);
+            case 2: return launchTransitionMmaT<2>(in, dProbIdx, dEigenIdx, dRateSet, dLengths, count);
+            case 3: return launchTransitionMmaT<3>(in, dProbIdx, dEigenIdx, dRateSet, dLengths, count);
+            case 4: return launchTransitionMmaT<4>(in, dProbIdx, dEigenIdx, dRateSet, dLengths, count);
+            case 8: return launchTransitionMmaT<8>(in, dProbIdx, dEigenIdx, dRateSet, dLengths, count);
+            default: break;
+        }
+    }
     size_t smem = (size_t)in->S * (2 * sizeof(double) + sizeof(int)) + 16;
     int threads = in->Sp * in->Sp >= 1024 ? 256 : (in->Sp * in->Sp >= 128 ? 128 : 32);
     dim3 grid(count, in->C);
@@ -598,10 +687,6 @@ k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int
 // exactly once per op, so there is nothing to stage), B fragments from the row-major matrix staged in
 // shared memory with a (Sp+4)-double row stride (conflict-free for the 8x4 fragment shape), and the
 // 16 x Sp accumulator tile of each warp lives in registers.  Block = 4 warps x 16 patterns.
-__device__ __forceinline__ void dmma884acc(double& d0, double& d1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 template <int NT>
 __global__ void __launch_bounds__(128)
