@@ -261,6 +261,9 @@ void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder,
         }
         // retire this phase's ops only now, so that maximality was judged on a consistent snapshot
         for (int q = plan.subs[plan.phaseStart.back()].begin; q < (int)plan.order.size(); ++q) alive[plan.order[q]] = 0;
+        // longest subtrees first: blocks are dispatched in grid order, so the long walks start early
+        std::stable_sort(plan.subs.begin() + plan.phaseStart.back(), plan.subs.end(),
+                         [](const Sub& a, const Sub& b) { return (a.end - a.begin) > (b.end - b.begin); });
         remaining = n - (int)plan.order.size();
         plan.phaseStart.push_back((int)plan.subs.size());
     }
@@ -500,10 +503,10 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->reorder = envInt("B200_REORDER", 1);
     in->phaseT = envInt("B200_PHASE_T", 0);
     in->phaseTmin = std::max(1, envInt("B200_PHASE_TMIN", 4));
-    in->phaseOversub = std::max(1, envInt("B200_PHASE_OVERSUB", 3));
-    in->walkMinBlocks = envInt("B200_WALK_MINB", 5);
+    in->phaseOversub = std::max(1, envInt("B200_PHASE_OVERSUB", 2));
+    in->walkMinBlocks = envInt("B200_WALK_MINB", 4);
     in->genericMma = envInt("B200_GENERIC_MMA", 1);
-    in->walkR = envInt("B200_WALK_R", 2);
+    in->walkR = envInt("B200_WALK_R", 4);
     if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4) in->walkR = 2;
     in->stackDepthMax = std::min(64, std::max(0, envInt("B200_STACK_DEPTH", 12)));
 

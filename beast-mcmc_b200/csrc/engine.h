@@ -103,10 +103,10 @@ struct Instance {
     int walkVariant = 0;
     int reorder = 1;
     int stackDepthMax = 12;
-    int walkMinBlocks = 5;       // __launch_bounds__(128, n) variant of the 4-state walk (4, 5 or 6)
+    int walkMinBlocks = 4;       // __launch_bounds__(128, n) variant of the 4-state walk (4, 5 or 6)
     int genericMma = 1;          // S > 4: 1 = fp64 tensor-core block walk, 0 = FMA block walk
-    int walkR = 2;               // patterns per thread in the 4-state walk (1, 2 or 4)
-    int phaseTmin = 4, phaseOversub = 4;
+    int walkR = 4;               // patterns per thread in the 4-state walk (1, 2 or 4)
+    int phaseTmin = 4, phaseOversub = 2;
     int phaseT = 0;              // max ops per subtree walk (0 = automatic)
 };
 

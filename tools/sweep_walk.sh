@@ -3,7 +3,7 @@
 # columns: variant(0 global,1 stack) reorder minBlocks stackDepth phaseT(0=auto) R(patterns/thread) Tmin oversub
 mkdir -p gpurun_out
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1   # builds the alignment cache
-CFGS=${CFGS:-"2 1 5 12 0 1 4 3;2 1 5 12 0 2 4 3;0 1 5 12 0 2 4 3;2 1 5 12 0 2 4 2;2 1 5 12 0 2 4 6;2 1 5 12 0 2 8 3;2 1 5 12 0 1 4 6"}
+CFGS=${CFGS:-"0 1 5 12 0 2 4 3;0 1 5 12 0 2 4 2;0 1 5 12 0 2 8 2;0 1 4 12 0 4 4 2;0 1 5 12 0 2 16 2;0 1 5 12 0 2 4 1"}
 IFS=';' read -ra LIST <<< "$CFGS"
 for cfg in "${LIST[@]}"; do
   set -- $cfg
