@@ -193,7 +193,7 @@ struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; };
 //     shared-memory stack.
 // Lists with hazards the forest model does not cover (a buffer written twice, read-before-write,
 // a result consumed by two ops) run as ONE subtree in the caller's order.
-struct Sub { int begin, end; };
+struct Sub { int begin, end, pBase, pLimit; };     // op positions [begin,end) applied to patterns [pBase,pLimit)
 struct Plan {
     std::vector<int> order;          // execution position -> index into the caller's list
     std::vector<Sub> subs;           // position ranges, grouped by phase
@@ -206,7 +206,7 @@ void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder,
     auto single = [&]() {
         plan.order.resize(n);
         for (int k = 0; k < n; ++k) plan.order[k] = k;
-        plan.subs.assign(1, Sub{0, n});
+        plan.subs.assign(1, Sub{0, n, 0, 0});
         plan.phaseStart = {0, 1};
     };
     if (!allowReorder || n < 2) { single(); return; }
@@ -230,7 +230,8 @@ void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder,
     int remaining = n;
     while (remaining > 0) {
         // per-phase subtree bound: enough subtrees to fill the machine, re-evaluated on what is left
-        const int T = fixedT > 0 ? fixedT : std::max(minT, (remaining + wantSubs - 1) / wantSubs);
+        // (a remainder of a couple of dozen ops is cheaper as one launch than as several tiny phases)
+        const int T = fixedT > 0 ? fixedT : (remaining <= 24 ? remaining : std::max(minT, (remaining + wantSubs - 1) / wantSubs));
         for (int k = 0; k < n; ++k) {
             if (!alive[k]) continue;
             const int a = (ch0[k] >= 0 && alive[ch0[k]]) ? ch0[k] : -1;
@@ -257,7 +258,7 @@ void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder,
                 if (na >= nb) { if (b >= 0) stack.push_back({b, 0}); if (a >= 0) stack.push_back({a, 0}); }
                 else          { if (a >= 0) stack.push_back({a, 0}); if (b >= 0) stack.push_back({b, 0}); }
             }
-            plan.subs.push_back(Sub{begin, (int)plan.order.size()});
+            plan.subs.push_back(Sub{begin, (int)plan.order.size(), 0, 0});
         }
         // retire this phase's ops only now, so that maximality was judged on a consistent snapshot
         for (int q = plan.subs[plan.phaseStart.back()].begin; q < (int)plan.order.size(); ++q) alive[plan.order[q]] = 0;
@@ -292,21 +293,62 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     }
     const bool fourState = in->matCP > 0;
     Plan plan;
+    int maxWindow = in->Ppad;
     {
-        // enough (subtree x tile) walks to put ~32 warps on every SM, 4x oversubscribed for balance
-        // patterns one warp owns: FMA kernel (32/CP)*R, tensor kernel 8*R (all categories)
+        // patterns one warp owns: FMA kernel (32/CP)*R, tensor kernels 8*R resp. 16
         const int patsPerWarp = !fourState ? 16 : (in->walkVariant == 2 ? 8 * std::min(in->walkR, 2) : (32 / in->matCP) * in->walkR);
-        const int warpsPerSub = std::max(1, (in->Ppad + patsPerWarp - 1) / patsPerWarp);
         const int warpsPerSM = fourState ? 32 : 12;      // resident warps the kernel family can hold per SM
-        const int wantSubs = std::max(1, in->phaseOversub * ((in->smCount * warpsPerSM + warpsPerSub - 1) / warpsPerSub));
-        planPhases(hops, in->nBuffers, in->reorder && !byPartition, in->phaseT, wantSubs, in->phaseTmin, plan);
+        auto wantSubsFor = [&](int window) {
+            const int warpsPerSub = std::max(1, (window + patsPerWarp - 1) / patsPerWarp);
+            // enough (subtree x tile) walks to fill every SM, oversubscribed for balance
+            return std::max(1, in->phaseOversub * ((in->smCount * warpsPerSM + warpsPerSub - 1) / warpsPerSub));
+        };
+        if (!byPartition) {
+            planPhases(hops, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(in->Ppad), in->phaseTmin, plan);
+            for (Sub& sb : plan.subs) { sb.pBase = 0; sb.pLimit = in->Ppad; }
+        } else {
+            // partitions are independent (disjoint pattern windows): plan each one on its own and merge the
+            // plans phase by phase; every subtree carries its partition's pattern window
+            std::vector<std::vector<int>> members(in->partitionCount);
+            for (int k = 0; k < n; ++k) members[hops[k].part].push_back(k);
+            std::vector<Plan> plans;
+            std::vector<int> base;
+            maxWindow = 1;
+            for (int part = 0; part < in->partitionCount; ++part) {
+                if (members[part].empty()) continue;
+                std::vector<HostOp> sub(members[part].size());
+                for (size_t q = 0; q < sub.size(); ++q) sub[q] = hops[members[part][q]];
+                Plan pl;
+                const int window = in->partEnd[part] - in->partBegin[part];
+                planPhases(sub, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(std::max(1, window)), in->phaseTmin, pl);
+                base.push_back((int)plan.order.size());
+                for (int idx : pl.order) plan.order.push_back(members[part][idx]);
+                for (Sub& sb : pl.subs) {
+                    sb.begin += base.back(); sb.end += base.back();
+                    sb.pBase = in->partBegin[part]; sb.pLimit = in->partEnd[part];
+                }
+                maxWindow = std::max(maxWindow, window);
+                plans.push_back(std::move(pl));
+            }
+            plan.phaseStart.assign(1, 0);
+            for (size_t ph = 0;; ++ph) {
+                bool any = false;
+                for (const Plan& pl : plans) {
+                    if (ph + 1 >= pl.phaseStart.size()) continue;
+                    any = true;
+                    for (int q = pl.phaseStart[ph]; q < pl.phaseStart[ph + 1]; ++q) plan.subs.push_back(pl.subs[q]);
+                }
+                if (!any) break;
+                plan.phaseStart.push_back((int)plan.subs.size());
+            }
+        }
     }
     const std::vector<int>& order = plan.order;
 
     // ---- stack slots (4-state path only): one backward pass finds, for every produced value, the
     // position of its LAST reader inside this list (before the buffer is re-written); the forward
     // pass then parks results in slots and frees each slot at that last read.
-    const int maxDepth = (fourState && !byPartition && in->walkVariant == 1) ? in->stackDepthMax : 0;
+    const int maxDepth = (fourState && in->walkVariant == 1) ? in->stackDepthMax : 0;
     std::vector<int> lastReadOfProd(maxDepth > 0 ? n : 0, -1);
     std::vector<int> subOfPos(n, 0);
     for (int sIdx = 0; sIdx < (int)plan.subs.size(); ++sIdx)
@@ -411,8 +453,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         const int s0 = plan.phaseStart[ph], s1 = plan.phaseStart[ph + 1];
         if (s1 <= s0) continue;
         TimedScope ts(in, T_PARTIALS);
-        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int2*>(dSubs) + s0, s1 - s0, depthUsed)
-                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int2*>(dSubs) + s0, s1 - s0);
+        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, depthUsed, maxWindow)
+                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, maxWindow);
     }
     if (tmp != nullptr) { cudaStreamSynchronize(in->stream); cudaFree(tmp); }
     CUDA_OK(e);

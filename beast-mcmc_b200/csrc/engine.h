@@ -113,8 +113,9 @@ struct Instance {
 // ---- kernel launchers (kernels.cu) -----------------------------------------------------------
 cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const int* dEigenIdx,
                                      const int* dRateSet, const double* dLengths, int count);
-cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth);
-cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int2* dSubs, int nSubs);
+// dSubs[k] = (first op, one-past-last op, first pattern, one-past-last pattern) of subtree walk k
+cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow);
+cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow);
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
                        const double* cumScale, int pBegin, int pEnd, double* dOutSlot);
 cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,

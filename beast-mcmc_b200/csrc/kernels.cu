@@ -218,7 +218,7 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
 //   * tip states: one byte per pattern, fetched one op ahead
 struct WalkArgs {
     const Op4* ops;
-    const int2* subs;          // [subtree] = (first, one-past-last) position in ops
+    const int4* subs;          // [subtree] = (first op, one-past-last op, first pattern, one-past-last pattern)
     double* partials;          // slab base
     size_t stride;             // elements per slot
     const uint8_t* states;     // [tip][Ppad]
@@ -276,8 +276,8 @@ __device__ __forceinline__ void childTerm(const WalkArgs& A, int child, int matI
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int p = p0 + r * G;
-            const bool active = catValid && p < A.Ppad && p >= pBegin && p < pEnd;
-            const int s = active ? (int)__ldg(t + (p < A.Ppad ? p : 0)) : S;
+            const bool active = catValid && p >= pBegin && p < pEnd;
+            const int s = active ? (int)__ldg(t + p) : S;
             double v[4];
             if (s < S) ldg256_ro(m + 4 * CP * s, v);
             else {
@@ -294,7 +294,7 @@ __device__ __forceinline__ void childTerm(const WalkArgs& A, int child, int matI
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int p = p0 + r * G;
-            const bool active = catValid && p < A.Ppad && p >= pBegin && p < pEnd;
+            const bool active = catValid && p >= pBegin && p < pEnd;
             double x[4], v[4];
             if (STACK && slot != 0xFF) {
                 double2 lo = stackMem[((slot * R + r) * 2 + 0) * nthreads + threadIdx.x];
@@ -318,13 +318,15 @@ k_walk4(const WalkArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int c = lane / G;
-    const int p0 = warp * (G * R) + (lane % G);          // patterns p0 + r*G
+    const int4 range = __ldg(A.subs + blockIdx.y);
+    const int p0 = range.z + warp * (G * R) + (lane % G);          // patterns p0 + r*G
+    if (range.z + warp * (G * R) >= range.w) return;               // whole warp outside this subtree's pattern window
+    // (every op of a subtree carries the same [pBegin,pEnd) as the window, so the per-op range test suffices below)
     const bool catValid = c < A.C;
     const int cc = catValid ? c : 0;
     const size_t off0 = ((size_t)cc * A.Ppad + p0) * 4;
     const int moff = cc * 4;
     const int nthreads = blockDim.x;
-    const int2 range = __ldg(A.subs + blockIdx.y);
     const int last = range.y - 1;
 
     Op4 cur = loadOp(A.ops + range.x);
@@ -338,7 +340,7 @@ k_walk4(const WalkArgs A) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int p = p0 + r * G;
-            const bool active = catValid && p < A.Ppad && p >= cur.pBegin && p < cur.pEnd;
+            const bool active = catValid && p >= cur.pBegin && p < cur.pEnd;
             // ---- rescaling (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE) -----
             if (cur.sw >= 0) {
                 double m = active ? fmax(fmax(d[r][0], d[r][1]), fmax(d[r][2], d[r][3])) : 0.0;
@@ -383,9 +385,9 @@ static cudaError_t launchWalk4K(Instance* in, const WalkArgs& A, dim3 grid, size
 }
 
 template <int CP, int R>
-static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth) {
+static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow) {
     constexpr int G = 32 / CP;
-    const int warps = (in->Ppad + G * R - 1) / (G * R);
+    const int warps = (maxWindow + G * R - 1) / (G * R);
     dim3 grid((warps + 3) / 4, nSubs);
     WalkArgs A;
     A.ops = dOps; A.subs = dSubs; A.partials = in->partialsBase; A.stride = in->partialsElems;
@@ -421,10 +423,12 @@ k_walk4m(const WalkArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int pBase = warp * (8 * R) + g;                  // pattern of tile r: pBase + 8 r
+    const int4 range = __ldg(A.subs + blockIdx.y);
+    const int pLimit = range.w;
+    if (range.z + warp * (8 * R) >= pLimit) return;
+    const int pBase = range.z + warp * (8 * R) + g;        // pattern of tile r: pBase + 8 r
     const int S = A.S, C = A.C;
     const size_t mstride = A.matStride;
-    const int2 range = __ldg(A.subs + blockIdx.y);
     const int last = range.y - 1;
     const size_t catStride = (size_t)A.Ppad * 4;
 
@@ -436,7 +440,7 @@ k_walk4m(const WalkArgs A) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int p = pBase + 8 * r;
-            act[r] = p < A.Ppad && p >= cur.pBegin && p < cur.pEnd;
+            act[r] = p < pLimit && p >= cur.pBegin && p < cur.pEnd;
         }
 #pragma unroll
         for (int child = 0; child < 2; ++child) {
@@ -532,8 +536,8 @@ k_walk4m(const WalkArgs A) {
 }
 
 template <int CMAX, int R>
-static cudaError_t launchWalk4M(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs) {
-    const int warps = (in->Ppad + 8 * R - 1) / (8 * R);
+static cudaError_t launchWalk4M(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int maxWindow) {
+    const int warps = (maxWindow + 8 * R - 1) / (8 * R);
     dim3 grid((warps + 3) / 4, nSubs);
     WalkArgs A;
     A.ops = dOps; A.subs = dSubs; A.partials = in->partialsBase; A.stride = in->partialsElems;
@@ -544,37 +548,37 @@ static cudaError_t launchWalk4M(Instance* in, const Op4* dOps, const int2* dSubs
     return cudaGetLastError();
 }
 
-static cudaError_t launchWalk4Mma(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs) {
+static cudaError_t launchWalk4Mma(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     const bool r2 = in->walkR >= 2;
     switch (in->matCP) {
-        case 1: return r2 ? launchWalk4M<1, 2>(in, dOps, dSubs, nSubs) : launchWalk4M<1, 1>(in, dOps, dSubs, nSubs);
-        case 2: return r2 ? launchWalk4M<2, 2>(in, dOps, dSubs, nSubs) : launchWalk4M<2, 1>(in, dOps, dSubs, nSubs);
-        case 4: return r2 ? launchWalk4M<4, 2>(in, dOps, dSubs, nSubs) : launchWalk4M<4, 1>(in, dOps, dSubs, nSubs);
-        case 8: return r2 ? launchWalk4M<8, 2>(in, dOps, dSubs, nSubs) : launchWalk4M<8, 1>(in, dOps, dSubs, nSubs);
-        case 16: return launchWalk4M<16, 1>(in, dOps, dSubs, nSubs);
-        default: return launchWalk4M<32, 1>(in, dOps, dSubs, nSubs);
+        case 1: return r2 ? launchWalk4M<1, 2>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4M<1, 1>(in, dOps, dSubs, nSubs, maxWindow);
+        case 2: return r2 ? launchWalk4M<2, 2>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4M<2, 1>(in, dOps, dSubs, nSubs, maxWindow);
+        case 4: return r2 ? launchWalk4M<4, 2>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4M<4, 1>(in, dOps, dSubs, nSubs, maxWindow);
+        case 8: return r2 ? launchWalk4M<8, 2>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4M<8, 1>(in, dOps, dSubs, nSubs, maxWindow);
+        case 16: return launchWalk4M<16, 1>(in, dOps, dSubs, nSubs, maxWindow);
+        default: return launchWalk4M<32, 1>(in, dOps, dSubs, nSubs, maxWindow);
     }
 }
 
 template <int CP>
-static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth) {
+static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow) {
     switch (in->walkR) {
-        case 4: return launchWalk4R<CP, 4>(in, dOps, dSubs, nSubs, stackDepth);
-        case 2: return launchWalk4R<CP, 2>(in, dOps, dSubs, nSubs, stackDepth);
-        default: return launchWalk4R<CP, 1>(in, dOps, dSubs, nSubs, stackDepth);
+        case 4: return launchWalk4R<CP, 4>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        case 2: return launchWalk4R<CP, 2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        default: return launchWalk4R<CP, 1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
     }
 }
 
-cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int2* dSubs, int nSubs, int stackDepth) {
+cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow) {
     if (nSubs <= 0) return cudaSuccess;
-    if (in->walkVariant == 2) return launchWalk4Mma(in, dOps, dSubs, nSubs);
+    if (in->walkVariant == 2) return launchWalk4Mma(in, dOps, dSubs, nSubs, maxWindow);
     switch (in->matCP) {
-        case 1: return launchWalk4T<1>(in, dOps, dSubs, nSubs, stackDepth);
-        case 2: return launchWalk4T<2>(in, dOps, dSubs, nSubs, stackDepth);
-        case 4: return launchWalk4T<4>(in, dOps, dSubs, nSubs, stackDepth);
-        case 8: return launchWalk4T<8>(in, dOps, dSubs, nSubs, stackDepth);
-        case 16: return launchWalk4T<16>(in, dOps, dSubs, nSubs, stackDepth);
-        default: return launchWalk4T<32>(in, dOps, dSubs, nSubs, stackDepth);
+        case 1: return launchWalk4T<1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        case 2: return launchWalk4T<2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        case 4: return launchWalk4T<4>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        case 8: return launchWalk4T<8>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        case 16: return launchWalk4T<16>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        default: return launchWalk4T<32>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
     }
 }
 
@@ -586,7 +590,7 @@ cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int2* dSubs, int nS
 // tile (thread index = pattern-major, parent state fastest: conflict-free matrix reads, broadcast
 // child reads, coalesced stores), tracks per-pattern maxima for the optional rescale.
 __global__ void __launch_bounds__(256)
-k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int S, int Sp, int C, int Ppad, int TP,
+k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int Sp, int C, int Ppad, int TP,
                int logScalers, int stageMatrices) {
     extern __shared__ double smg[];
     const size_t msz = stageMatrices ? (size_t)Sp * Sp : 0;
@@ -595,10 +599,11 @@ k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int
     double* x1 = smg + 2 * msz;
     double* x2 = x1 + (size_t)TP * Sp;
     unsigned long long* pmax = reinterpret_cast<unsigned long long*>(x2 + (size_t)TP * Sp);
-    const int p0 = blockIdx.x * TP;
+    const int4 range = subs[blockIdx.y];
+    const int p0 = range.z + blockIdx.x * TP;
+    if (p0 >= range.w) return;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int tileElems = TP * Sp;
-    const int2 range = subs[blockIdx.y];
+    const int tileElems = min(TP, Ppad - p0) * Sp;          // never read past the slab's last pattern
 
     for (int k = range.x; k < range.y; ++k) {
         const DevOp op = ops[k];
@@ -620,7 +625,7 @@ k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int
             for (int q = tid; q < tileElems; q += nt) {
                 const int pl = q / Sp, i = q - pl * Sp;
                 const int p = p0 + pl;
-                const bool active = p >= op.pBegin && p < op.pEnd;
+                const bool active = p >= op.pBegin && p < op.pEnd && p < range.w;
                 if (!active) continue;
                 double a, b;
                 if (op.c1) {
@@ -651,7 +656,7 @@ k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int
                 for (int q = tid; q < tileElems; q += nt) {
                     const int pl = q / Sp;
                     const int p = p0 + pl;
-                    if (p < op.pBegin || p >= op.pEnd) continue;
+                    if (p < op.pBegin || p >= op.pEnd || p >= range.w) continue;
                     double f;
                     if (op.scaleWrite) {
                         f = __longlong_as_double((long long)pmax[pl]);
@@ -666,7 +671,7 @@ k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int
             if (op.scaleWrite) {
                 for (int pl = tid; pl < TP; pl += nt) {
                     const int p = p0 + pl;
-                    if (p < op.pBegin || p >= op.pEnd) continue;
+                    if (p < op.pBegin || p >= op.pEnd || p >= range.w) continue;
                     double m = __longlong_as_double((long long)pmax[pl]);
                     if (m == 0.0) m = 1.0;
                     const double lm = log(m);
@@ -690,7 +695,7 @@ k_walk_generic(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int
 
 template <int NT>
 __global__ void __launch_bounds__(128)
-k_walk_mma(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int S, int C, int Ppad, int logScalers) {
+k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int C, int Ppad, int logScalers) {
     constexpr int Sp = 8 * NT;
     constexpr int LD = Sp + 4;                       // shared-memory row stride (doubles)
     extern __shared__ double smm[];
@@ -698,8 +703,9 @@ k_walk_mma(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int S, 
     double* P2 = smm + Sp * LD;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int pw = blockIdx.x * 64 + w * 16;         // first pattern of this warp's 16-row tile
-    const int2 range = subs[blockIdx.y];
+    const int4 range = subs[blockIdx.y];
+    if (range.z + blockIdx.x * 64 >= range.w) return;      // block outside this subtree's pattern window
+    const int pw = range.z + blockIdx.x * 64 + w * 16;     // first pattern of this warp's 16-row tile
     const size_t mRow = (size_t)C * Sp * Sp;         // offset of the row-major copies in a matrix buffer
 
     for (int k = range.x; k < range.y; ++k) {
@@ -708,7 +714,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int S, 
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             const int p = pw + 8 * m + g;
-            act[m] = p < Ppad && p >= op.pBegin && p < op.pEnd;
+            act[m] = p < range.w && p >= op.pBegin && p < op.pEnd;
         }
         double rowMax[2] = {0.0, 0.0};
         for (int c = 0; c < C; ++c) {
@@ -828,7 +834,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int2* __restrict__ subs, int S, 
 }
 
 template <int NT>
-static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int2* dSubs, int nSubs) {
+static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     constexpr int Sp = 8 * NT;
     const size_t smem = 2 * (size_t)Sp * (Sp + 4) * sizeof(double);
     if (smem > in->mmaSmemConfigured) {
@@ -836,20 +842,20 @@ static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int2* d
         if (e != cudaSuccess) return e;
         in->mmaSmemConfigured = smem;
     }
-    dim3 grid((in->Ppad + 63) / 64, nSubs);
+    dim3 grid((maxWindow + 63) / 64, nSubs);
     k_walk_mma<NT><<<grid, 128, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
     return cudaGetLastError();
 }
 
-cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int2* dSubs, int nSubs) {
+cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     if (nSubs <= 0) return cudaSuccess;
     if (in->genericMma) {
         switch (in->Sp / 8) {
-            case 1: return launchWalkMmaT<1>(in, dOps, dSubs, nSubs);
-            case 2: return launchWalkMmaT<2>(in, dOps, dSubs, nSubs);
-            case 3: return launchWalkMmaT<3>(in, dOps, dSubs, nSubs);
-            case 4: return launchWalkMmaT<4>(in, dOps, dSubs, nSubs);
-            case 8: return launchWalkMmaT<8>(in, dOps, dSubs, nSubs);
+            case 1: return launchWalkMmaT<1>(in, dOps, dSubs, nSubs, maxWindow);
+            case 2: return launchWalkMmaT<2>(in, dOps, dSubs, nSubs, maxWindow);
+            case 3: return launchWalkMmaT<3>(in, dOps, dSubs, nSubs, maxWindow);
+            case 4: return launchWalkMmaT<4>(in, dOps, dSubs, nSubs, maxWindow);
+            case 8: return launchWalkMmaT<8>(in, dOps, dSubs, nSubs, maxWindow);
             default: break;      // other state counts: FMA block walk below
         }
     }
@@ -866,7 +872,7 @@ cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int2* dSubs
         if (e != cudaSuccess) return e;
         in->genericSmemConfigured = smem;
     }
-    dim3 grid((in->Ppad + TP - 1) / TP, nSubs);
+    dim3 grid((maxWindow + TP - 1) / TP, nSubs);
     k_walk_generic<<<grid, 256, smem, in->stream>>>(dOps, dSubs, in->S, Sp, in->C, in->Ppad, TP,
                                                       in->logScalers ? 1 : 0, stage);
     return cudaGetLastError();

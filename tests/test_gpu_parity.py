@@ -219,6 +219,22 @@ def test_by_partition_equals_separate_instances():
                                              byPart, total)
     assert _rel(byPart[0], separate[0]) <= REL and _rel(byPart[1], separate[1]) <= REL
     assert _rel(total[0], sum(separate)) <= REL
+
+    # same list with per-partition rescaling (MPDLD:972-1017): scaleWrite per node, cumulative buffer per partition
+    internal = [node for node, _, _ in like.nodeOperations]
+    ops = []
+    for node, c1, c2 in like.nodeOperations:
+        for k in range(2):
+            ops += [node, node - N, -1, c1, c1 + k * nodeCount, c2, c2 + k * nodeCount, k, -1]
+    b.updatePartialsByPartition(np.array(ops, dtype=np.int32), len(ops) // 9)
+    cum = [2 * N - 2, 2 * N - 1]
+    for k in range(2):
+        b.resetScaleFactorsByPartition(cum[k], k)
+        b.accumulateScaleFactorsByPartition(np.array([n - N for n in internal], dtype=np.int32), len(internal), cum[k], k)
+    b.calculateRootLogLikelihoodsByPartition(root, np.array([0, 1], dtype=np.int32), np.array([0, 1], dtype=np.int32),
+                                             np.array(cum, dtype=np.int32), np.array([0, 1], dtype=np.int32), 2, 1,
+                                             byPart, total)
+    assert _rel(byPart[0], separate[0]) <= REL and _rel(byPart[1], separate[1]) <= REL
     b.finalize()
 
 
