@@ -473,6 +473,13 @@ def main():
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     # updatePartials is one launch per phase of independent subtrees; the roofline unit is the whole
     # operation list (all its launches) of one step
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get(args.workload)
+        if tj and all(getattr(args, k) is None for k in ("taxa", "patterns", "categories", "states")):
+            traffic = tj["dram_bytes_read_per_step"] + tj["dram_bytes_write_per_step"]
+            traffic_src = tj["source"]
     k_avg_ms = k_ms / args.steps
     achieved = byt / (k_avg_ms * 1e-3) / 1e9
     line = dict(meta_base)
@@ -482,7 +489,7 @@ def main():
         "vs_baseline": None, "logL": joint, "joint_evals_per_s": args.steps / (dev_ms * 1e-3),
         "roofline": {"bound": "hbm", "kernel": "k_walk4 (updatePartials, whole op list per launch)"
                      if S <= 4 else "k_walk_generic", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": byt, "algorithmic_flops_per_step": flo,
                      "gflops": flo / (k_avg_ms * 1e-3) / 1e9, "partials_ms_per_step": k_avg_ms,
                      "launches_per_step": k_n / args.steps,
