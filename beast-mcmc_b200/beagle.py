@@ -160,6 +160,7 @@ _SIGNATURES = {
     "beagleCalculateRootLogLikelihoods": ([_I, _IP, _IP, _IP, _IP, _I, _DP], _I),
     "beagleCalculateRootLogLikelihoodsByPartition": ([_I, _IP, _IP, _IP, _IP, _IP, _I, _I, _DP, _DP], _I),
     "beagleGetSiteLogLikelihoods": ([_I, _DP], _I),
+    "beagleCalculateEdgeDerivatives": ([_I, _IP, _IP, _IP, _IP, _I, _DP, _DP, _DP], _I),
     "b200SetKernelTiming": ([_I, _I], _I),
     "b200GetKernelTiming": ([_I, _I, _DP, C.POINTER(C.c_long)], _I),
     "b200HostAlloc": ([_L], C.c_void_p),
@@ -324,6 +325,27 @@ class BeagleJNIImpl(Beagle):
                     self._lib.beagleUpdateTransitionMatricesWithMultipleModels(
                         self.instance, _ip(eigenIndices)[1], _ip(categoryRateIndices)[1], _ip(probabilityIndices)[1],
                         d1[1] if d1 else None, d2[1] if d2 else None, _dp(edgeLengths)[1], count))
+
+    def setDifferentialMatrix(self, matrixIndex, inMatrix):
+        self._check("setDifferentialMatrix", self._lib.beagleSetDifferentialMatrix(self.instance, matrixIndex, _dp(inMatrix)[1]))
+
+    def transposeTransitionMatrices(self, inputIndices, resultIndices, matrixCount):
+        self._check("transposeTransitionMatrices",
+                    self._lib.beagleTransposeTransitionMatrices(self.instance, _ip(inputIndices)[1], _ip(resultIndices)[1], matrixCount))
+
+    def updatePrePartials(self, operations, operationCount, cumulativeScaleIndex):
+        self._check("updatePrePartials", self._lib.beagleUpdatePrePartials(self.instance, _ip(operations)[1],
+                                                                           operationCount, cumulativeScaleIndex))
+
+    def calculateEdgeDifferentials(self, postBufferIndices, preBufferIndices, derivativeMatrixIndices,
+                                   categoryWeightsIndices, count, outDerivatives, outSumDerivatives,
+                                   outSumSquaredDerivatives):
+        ptr = lambda a: None if a is None else a.ctypes.data_as(_DP)
+        self._check("calculateEdgeDifferentials",
+                    self._lib.beagleCalculateEdgeDerivatives(self.instance, _ip(postBufferIndices)[1], _ip(preBufferIndices)[1],
+                                                             _ip(derivativeMatrixIndices)[1], _ip(categoryWeightsIndices)[1],
+                                                             count, ptr(outDerivatives), ptr(outSumDerivatives),
+                                                             ptr(outSumSquaredDerivatives)))
 
     def updatePartials(self, operations, operationCount, cumulativeScaleIndex):
         self._check("updatePartials", self._lib.beagleUpdatePartials(self.instance, _ip(operations)[1],

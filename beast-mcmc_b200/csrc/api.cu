@@ -177,7 +177,7 @@ char gImplName[] = "B200-CUDA-Double";
 char gImplDesc[] = "sm_100a walk kernels: one launch per operation list, shared-memory operand stack";
 
 // ---- op planning ------------------------------------------------------------------------------
-struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; };
+struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; int kind = 0; };   // kind 1 = pre-order op
 
 // Execution plan of one operation list.
 //
@@ -270,6 +270,36 @@ void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder,
     }
 }
 
+// Pre-order lists form an OUT-forest (pre[node] needs pre[parent]); ops of equal depth are independent.
+// One launch per depth level, every op its own walk (grid.y = ops of the level).
+void planLevels(const std::vector<HostOp>& ops, int nBuffers, Plan& plan) {
+    const int n = (int)ops.size();
+    std::vector<int> writer(nBuffers, -1), level(n, 0);
+    bool hazard = false;
+    for (int k = 0; k < n; ++k) { if (writer[ops[k].dest] >= 0) hazard = true; writer[ops[k].dest] = k; }
+    int maxLevel = 0;
+    for (int k = 0; k < n && !hazard; ++k) {
+        for (int src : {ops[k].c1, ops[k].c2}) {
+            const int w = writer[src];
+            if (w < 0) continue;
+            if (w >= k) { hazard = true; break; }
+            level[k] = std::max(level[k], level[w] + 1);
+        }
+        maxLevel = std::max(maxLevel, level[k]);
+    }
+    plan.order.resize(n);
+    for (int k = 0; k < n; ++k) plan.order[k] = k;
+    plan.subs.clear();
+    if (hazard) { plan.subs.assign(1, Sub{0, n, 0, 0}); plan.phaseStart = {0, 1}; return; }
+    std::stable_sort(plan.order.begin(), plan.order.end(), [&](int a, int b) { return level[a] < level[b]; });
+    plan.phaseStart.assign(1, 0);
+    for (int pos = 0; pos < n; ++pos) {
+        if (pos > 0 && level[plan.order[pos]] != level[plan.order[pos - 1]]) plan.phaseStart.push_back((int)plan.subs.size());
+        plan.subs.push_back(Sub{pos, pos + 1, 0, 0});
+    }
+    plan.phaseStart.push_back((int)plan.subs.size());
+}
+
 int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartition) {
     const int n = (int)hops.size();
     if (n == 0) return BEAGLE_SUCCESS;
@@ -288,6 +318,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         in->states32[o.dest] = nullptr;
     }
     for (const HostOp& o : hops) {
+        if (o.kind == 1 && (in->partials[o.c1] == nullptr || in->states32[o.c1] != nullptr)) return BEAGLE_ERROR_OUT_OF_RANGE;
         if (in->partials[o.c1] == nullptr && in->states32[o.c1] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
         if (in->partials[o.c2] == nullptr && in->states32[o.c2] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
     }
@@ -304,7 +335,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             return std::max(1, in->phaseOversub * ((in->smCount * warpsPerSM + warpsPerSub - 1) / warpsPerSub));
         };
         if (!byPartition) {
-            planPhases(hops, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(in->Ppad), in->phaseTmin, plan);
+            if (hops[0].kind == 1) planLevels(hops, in->nBuffers, plan);
+            else planPhases(hops, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(in->Ppad), in->phaseTmin, plan);
             for (Sub& sb : plan.subs) { sb.pBase = 0; sb.pLimit = in->Ppad; }
         } else {
             // partitions are independent (disjoint pattern windows): plan each one on its own and merge the
@@ -348,7 +380,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     // ---- stack slots (4-state path only): one backward pass finds, for every produced value, the
     // position of its LAST reader inside this list (before the buffer is re-written); the forward
     // pass then parks results in slots and frees each slot at that last read.
-    const int maxDepth = (fourState && in->walkVariant == 1) ? in->stackDepthMax : 0;
+    const bool preOrder = hops[0].kind == 1;
+    const int maxDepth = (fourState && in->walkVariant == 1 && !preOrder) ? in->stackDepthMax : 0;
     std::vector<int> lastReadOfProd(maxDepth > 0 ? n : 0, -1);
     std::vector<int> subOfPos(n, 0);
     for (int sIdx = 0; sIdx < (int)plan.subs.size(); ++sIdx)
@@ -415,7 +448,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             d.m1 = o.m1; d.m2 = o.m2; d.sw = o.sw; d.sr = o.sr; d.cum = cum;
             d.pBegin = pBegin; d.pEnd = pEnd;
             d.slots = (unsigned)(srcSlot1 & 0xFF) | ((unsigned)(srcSlot2 & 0xFF) << 8) | ((unsigned)(dstSlot & 0xFF) << 16);
-            d.pad_ = 0;
+            d.pad_ = o.kind;
         } else {
             DevOp& d = dops[pos];
             memset(&d, 0, sizeof d);
@@ -431,6 +464,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             d.cumScale = cum >= 0 ? in->dScale + (size_t)cum * in->Ppad : nullptr;
             d.pBegin = pBegin; d.pEnd = pEnd;
             d.srcSlot1 = d.srcSlot2 = d.dstSlot = -1;
+            d.pad_ = o.kind;
         }
     }
     const void* hostOps = fourPath ? (const void*)ops4.data() : (const void*)dops.data();
@@ -453,8 +487,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         const int s0 = plan.phaseStart[ph], s1 = plan.phaseStart[ph + 1];
         if (s1 <= s0) continue;
         TimedScope ts(in, T_PARTIALS);
-        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, depthUsed, maxWindow)
-                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, maxWindow);
+        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, depthUsed, maxWindow, preOrder)
+                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, maxWindow, preOrder);
     }
     if (tmp != nullptr) { cudaStreamSynchronize(in->stream); cudaFree(tmp); }
     CUDA_OK(e);
@@ -899,10 +933,26 @@ int beagleGetTransitionMatrix(int instance, int matrixIndex, double* outMatrix) 
     return BEAGLE_SUCCESS;
 }
 
-int beagleSetDifferentialMatrix(int, int, const double*) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+int beagleSetDifferentialMatrix(int instance, int matrixIndex, const double* inMatrix) {
+    return beagleSetTransitionMatrix(instance, matrixIndex, inMatrix, 0.0);     // same storage, all layouts
+}
 int beagleConvolveTransitionMatrices(int, const int*, const int*, const int*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
 int beagleAddTransitionMatrices(int, const int*, const int*, const int*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
-int beagleTransposeTransitionMatrices(int, const int*, const int*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+int beagleTransposeTransitionMatrices(int instance, const int* inputIndices, const int* resultIndices, int matrixCount) {
+    GET_INSTANCE(in, instance);
+    std::vector<double> m((size_t)in->C * in->S * in->S), t(m.size());
+    for (int q = 0; q < matrixCount; ++q) {
+        int rc = beagleGetTransitionMatrix(instance, inputIndices[q], m.data());
+        if (rc != BEAGLE_SUCCESS) return rc;
+        for (int c = 0; c < in->C; ++c)
+            for (int i = 0; i < in->S; ++i)
+                for (int j = 0; j < in->S; ++j)
+                    t[((size_t)c * in->S + j) * in->S + i] = m[((size_t)c * in->S + i) * in->S + j];
+        rc = beagleSetTransitionMatrix(instance, resultIndices[q], t.data(), 0.0);
+        if (rc != BEAGLE_SUCCESS) return rc;
+    }
+    return BEAGLE_SUCCESS;
+}
 
 // ---- partials ---------------------------------------------------------------------------------
 int beagleUpdatePartials(int instance, const BeagleOperation* operations, int operationCount,
@@ -937,7 +987,18 @@ int beagleWaitForPartials(int instance, const int*, int) {
     return BEAGLE_SUCCESS;
 }
 
-int beagleUpdatePrePartials(int, const BeagleOperation*, int, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+int beagleUpdatePrePartials(int instance, const BeagleOperation* operations, int operationCount, int cumulativeScaleIndex) {
+    GET_INSTANCE(in, instance);
+    if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<HostOp> hops(operationCount);
+    for (int k = 0; k < operationCount; ++k) {
+        const BeagleOperation& o = operations[k];
+        hops[k] = {o.destinationPartials, o.destinationScaleWrite, o.destinationScaleRead, o.child1Partials,
+                   o.child1TransitionMatrix, o.child2Partials, o.child2TransitionMatrix, 0, cumulativeScaleIndex};
+        hops[k].kind = 1;
+    }
+    return planAndLaunch(in, hops, false);
+}
 int beagleUpdatePrePartialsByPartition(int, const BeagleOperationByPartition*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
 
 // ---- scale factors ----------------------------------------------------------------------------
@@ -1076,6 +1137,51 @@ int beagleGetSiteLogLikelihoods(int instance, double* outLogLikelihoods) {
     GET_INSTANCE(in, instance);
     CUDA_OK(cudaMemcpyAsync(outLogLikelihoods, in->dSite, sizeof(double) * in->P, cudaMemcpyDeviceToHost, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
+    return BEAGLE_SUCCESS;
+}
+
+// ---- edge derivatives (pre-order route) ---------------------------------------------------------
+int beagleCalculateEdgeDerivatives(int instance, const int* postBufferIndices, const int* preBufferIndices,
+                                   const int* derivativeMatrixIndices, const int* categoryWeightsIndices, int count,
+                                   double* outDerivatives, double* outSumDerivatives, double* outSumSquaredDerivatives) {
+    GET_INSTANCE(in, instance);
+    if (count <= 0) return BEAGLE_SUCCESS;
+    if (!validRange(categoryWeightsIndices[0], in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<EdgeRef> edges(count);
+    for (int e = 0; e < count; ++e) {
+        const int po = postBufferIndices[e], pr = preBufferIndices[e], dm = derivativeMatrixIndices[e];
+        if (!validRange(po, in->nBuffers) || !validRange(pr, in->nBuffers) || !validRange(dm, in->nMatrices) ||
+            in->partials[pr] == nullptr || (in->partials[po] == nullptr && in->states32[po] == nullptr))
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        edges[e].post = in->states32[po] != nullptr ? nullptr : in->partials[po];
+        edges[e].states = in->states32[po];
+        edges[e].pre = in->partials[pr];
+        edges[e].D = in->dMat + (size_t)dm * in->matStride;
+    }
+    void* dEdges = nullptr;
+    double* dOut = nullptr;
+    const size_t perEdge = outDerivatives != nullptr ? (size_t)in->P : 0;
+    CUDA_OK(cudaMalloc(&dEdges, sizeof(EdgeRef) * count));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dOut), sizeof(double) * ((size_t)count * (2 + perEdge)));
+    if (e != cudaSuccess) { cudaFree(dEdges); CUDA_OK(e); }
+    e = cudaMemcpyAsync(dEdges, edges.data(), sizeof(EdgeRef) * count, cudaMemcpyHostToDevice, in->stream);
+    if (e == cudaSuccess) {
+        TimedScope ts(in, T_ROOT);
+        e = launchEdgeDerivatives(in, static_cast<const EdgeRef*>(dEdges), count,
+                                  in->dWeights + (size_t)categoryWeightsIndices[0] * in->C,
+                                  perEdge ? dOut + 2 * (size_t)count : nullptr, dOut, dOut + count);
+    }
+    std::vector<double> host((size_t)count * (2 + perEdge));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), dOut, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, in->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(in->stream);
+    cudaFree(dEdges);
+    cudaFree(dOut);
+    CUDA_OK(e);
+    for (int k = 0; k < count; ++k) {
+        if (outSumDerivatives) outSumDerivatives[k] = host[k];
+        if (outSumSquaredDerivatives) outSumSquaredDerivatives[k] = host[count + k];
+    }
+    if (outDerivatives) memcpy(outDerivatives, host.data() + 2 * (size_t)count, sizeof(double) * (size_t)count * in->P);
     return BEAGLE_SUCCESS;
 }
 

@@ -45,6 +45,9 @@ struct alignas(16) Op4 {
     int pad_;
 };
 
+// one edge of a calculateEdgeDerivatives call
+struct EdgeRef { const double* post; const int* states; const double* pre; const double* D; };
+
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
 
 struct Instance {
@@ -114,8 +117,10 @@ struct Instance {
 cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const int* dEigenIdx,
                                      const int* dRateSet, const double* dLengths, int count);
 // dSubs[k] = (first op, one-past-last op, first pattern, one-past-last pattern) of subtree walk k
-cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow);
-cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow);
+cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder);
+cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow, bool preOrder);
+cudaError_t launchEdgeDerivatives(Instance* in, const EdgeRef* dEdges, int count, const double* weights, double* outPerPattern,
+                                  double* outSum, double* outSumSq);
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
                        const double* cumScale, int pBegin, int pEnd, double* dOutSlot);
 cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,

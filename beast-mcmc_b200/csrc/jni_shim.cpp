@@ -238,10 +238,13 @@ NATIVE(jint, calculateRootLogLikelihoodsByPartition)(JNIEnv* env, jobject, jint 
 NATIVE(jint, getSiteLogLikelihoods)(JNIEnv* env, jobject, jint instance, jdoubleArray out) {
     DblOut o(env, out); return beagleGetSiteLogLikelihoods(instance, o);
 }
-// derivative API: SURVEY.md 8f "next" rows
-NATIVE(jint, calculateEdgeDifferentials)(JNIEnv*, jobject, jint, jintArray, jintArray, jintArray, jintArray, jint,
-                                         jdoubleArray, jdoubleArray, jdoubleArray) {
-    return BEAGLE_ERROR_NO_IMPLEMENTATION;
+// remaining derivative API: SURVEY.md 8f "next" rows
+NATIVE(jint, calculateEdgeDifferentials)(JNIEnv* env, jobject, jint instance, jintArray post, jintArray pre, jintArray deriv,
+                                         jintArray weights, jint count, jdoubleArray out, jdoubleArray outSum,
+                                         jdoubleArray outSumSquared) {
+    IntIn a(env, post), b(env, pre), c(env, deriv), w(env, weights);
+    DblOut o(env, out), s1(env, outSum), s2(env, outSumSquared);
+    return beagleCalculateEdgeDerivatives(instance, a, b, c, w, count, o, s1, s2);
 }
 NATIVE(jint, calculateCrossProductDifferentials)(JNIEnv*, jobject, jint, jintArray, jintArray, jintArray, jintArray,
                                                  jdoubleArray, jint, jdoubleArray, jdoubleArray) {

@@ -334,8 +334,28 @@ k_walk4(const WalkArgs A) {
         const Op4 nxt = loadOp(A.ops + min(k + 1, last));      // one record ahead, off the dependent chain
         const int s1 = cur.slots & 0xFF, s2 = (cur.slots >> 8) & 0xFF, sd = (cur.slots >> 16) & 0xFF;
         double d[R][4];
-        childTerm<CP, R, STACK, true>(A, cur.c1, cur.m1, s1, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
-        childTerm<CP, R, STACK, false>(A, cur.c2, cur.m2, s2, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
+        if (cur.pad_ == 0) {
+            childTerm<CP, R, STACK, true>(A, cur.c1, cur.m1, s1, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
+            childTerm<CP, R, STACK, false>(A, cur.c2, cur.m2, s2, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
+        } else {
+            // pre-order op: q = pre[parent] (*) (M_sib post[sib]) at the parent, then down the node's own branch
+            // with the transposed matrix: pre[node][j] = sum_i q[i] M_node[i][j]
+            childTerm<CP, R, false, true>(A, cur.c2, cur.m2, 0xFF, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
+            Mat4 M1;
+            loadMat<CP>(A.mats + (size_t)cur.m1 * A.matStride + moff, M1);
+            const double* xg = A.partials + (size_t)cur.c1 * A.stride + off0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int p = p0 + r * G;
+                double x[4] = {0.0, 0.0, 0.0, 0.0};
+                if (catValid && p >= cur.pBegin && p < cur.pEnd) ldg256(xg + (size_t)r * G * 4, x);
+                double q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = x[i] * d[r][i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[r][j] = M1.r[j][0] * q[0] + M1.r[j][1] * q[1] + M1.r[j][2] * q[2] + M1.r[j][3] * q[3];
+            }
+        }
         double* dg = A.partials + (size_t)cur.dest * A.stride + off0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -569,9 +589,9 @@ static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int4* dSubs
     }
 }
 
-cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow) {
+cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder) {
     if (nSubs <= 0) return cudaSuccess;
-    if (in->walkVariant == 2) return launchWalk4Mma(in, dOps, dSubs, nSubs, maxWindow);
+    if (in->walkVariant == 2 && !preOrder) return launchWalk4Mma(in, dOps, dSubs, nSubs, maxWindow);
     switch (in->matCP) {
         case 1: return launchWalk4T<1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
         case 2: return launchWalk4T<2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
@@ -591,14 +611,15 @@ cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nS
 // child reads, coalesced stores), tracks per-pattern maxima for the optional rescale.
 __global__ void __launch_bounds__(256)
 k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int Sp, int C, int Ppad, int TP,
-               int logScalers, int stageMatrices) {
+               int logScalers, int stageMatrices, int hasPre) {
     extern __shared__ double smg[];
     const size_t msz = stageMatrices ? (size_t)Sp * Sp : 0;
     double* mt1s = smg;
     double* mt2s = smg + msz;
     double* x1 = smg + 2 * msz;
     double* x2 = x1 + (size_t)TP * Sp;
-    unsigned long long* pmax = reinterpret_cast<unsigned long long*>(x2 + (size_t)TP * Sp);
+    double* qt = x2 + (size_t)TP * Sp;                       // pre-order lists only: q tile
+    unsigned long long* pmax = reinterpret_cast<unsigned long long*>(qt + (hasPre ? (size_t)TP * Sp : 0));
     const int4 range = subs[blockIdx.y];
     const int p0 = range.z + blockIdx.x * TP;
     if (p0 >= range.w) return;
@@ -611,7 +632,9 @@ k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int
         if (doMax) for (int q = tid; q < TP; q += nt) pmax[q] = 0ull;
         for (int c = 0; c < C; ++c) {
             __syncthreads();
-            const double* m1g = op.m1 + (size_t)c * Sp * Sp;
+            const bool pre = op.pad_ == 1;
+            // pre-order ops use the ROW-MAJOR copy of the node's own matrix (second half of the buffer)
+            const double* m1g = op.m1 + (pre ? (size_t)C * Sp * Sp : 0) + (size_t)c * Sp * Sp;
             const double* m2g = op.m2 + (size_t)c * Sp * Sp;
             if (stageMatrices) {
                 for (int q = tid; q < Sp * Sp; q += nt) { mt1s[q] = m1g[q]; mt2s[q] = m2g[q]; }
@@ -622,6 +645,38 @@ k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int
             __syncthreads();
             const double* mt1 = stageMatrices ? mt1s : m1g;
             const double* mt2 = stageMatrices ? mt2s : m2g;
+            if (pre) {
+                // stage A: q[i] = pre[parent][i] * (M_sib post[sib])[i]
+                for (int q = tid; q < tileElems; q += nt) {
+                    const int pl = q / Sp, i = q - pl * Sp;
+                    const int p = p0 + pl;
+                    double b = 0.0;
+                    if (p >= op.pBegin && p < op.pEnd && p < range.w) {
+                        if (op.c2) {
+                            const double* xr = x2 + (size_t)pl * Sp;
+                            for (int j = 0; j < S; ++j) b += mt2[(size_t)j * Sp + i] * xr[j];
+                        } else {
+                            int s = static_cast<const int*>(op.s2)[p];
+                            b = (s < S) ? mt2[(size_t)s * Sp + i] : ((i < S) ? 1.0 : 0.0);
+                        }
+                        b *= x1[q];
+                    }
+                    qt[q] = b;
+                }
+                __syncthreads();
+                // stage B: pre[node][j] = sum_i q[i] M_node[i][j]   (row-major matrix: conflict-free in j)
+                for (int q = tid; q < tileElems; q += nt) {
+                    const int pl = q / Sp, j = q - pl * Sp;
+                    const int p = p0 + pl;
+                    if (!(p >= op.pBegin && p < op.pEnd && p < range.w)) continue;
+                    double d = 0.0;
+                    const double* qr = qt + (size_t)pl * Sp;
+                    for (int i = 0; i < S; ++i) d += qr[i] * mt1[(size_t)i * Sp + j];
+                    op.dest[tileOff + q] = d;
+                    if (doMax) atomicMax(&pmax[pl], (unsigned long long)__double_as_longlong(d));
+                }
+                continue;
+            }
             for (int q = tid; q < tileElems; q += nt) {
                 const int pl = q / Sp, i = q - pl * Sp;
                 const int p = p0 + pl;
@@ -847,9 +902,9 @@ static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int4* d
     return cudaGetLastError();
 }
 
-cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow) {
+cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow, bool preOrder) {
     if (nSubs <= 0) return cudaSuccess;
-    if (in->genericMma) {
+    if (in->genericMma && !preOrder) {
         switch (in->Sp / 8) {
             case 1: return launchWalkMmaT<1>(in, dOps, dSubs, nSubs, maxWindow);
             case 2: return launchWalkMmaT<2>(in, dOps, dSubs, nSubs, maxWindow);
@@ -861,12 +916,13 @@ cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs
     }
     const int Sp = in->Sp;
     const size_t budget = in->maxSmemOptin > 16384 ? in->maxSmemOptin - 2048 : 46000;
-    int stage = (2 * (size_t)Sp * Sp * 8 + 2 * 8 * (size_t)Sp * 8 + 64 <= budget) ? 1 : 0;
+    const int tiles = preOrder ? 3 : 2;
+    int stage = (2 * (size_t)Sp * Sp * 8 + (size_t)tiles * 8 * (size_t)Sp * 8 + 64 <= budget) ? 1 : 0;
     size_t fixed = stage ? 2 * (size_t)Sp * Sp * 8 : 0;
     int TP = 32;
-    while (TP > 1 && fixed + (size_t)TP * (2 * Sp + 1) * 8 > budget) TP >>= 1;
+    while (TP > 1 && fixed + (size_t)TP * (tiles * Sp + 1) * 8 > budget) TP >>= 1;
     while (TP > 8 && (in->Ppad + TP - 1) / TP < in->smCount) TP >>= 1;   // keep every SM busy
-    size_t smem = fixed + (size_t)TP * (2 * Sp + 1) * 8;
+    size_t smem = fixed + (size_t)TP * (tiles * Sp + 1) * 8;
     if (smem > in->genericSmemConfigured) {
         cudaError_t e = cudaFuncSetAttribute(k_walk_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -874,7 +930,87 @@ cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs
     }
     dim3 grid((maxWindow + TP - 1) / TP, nSubs);
     k_walk_generic<<<grid, 256, smem, in->stream>>>(dOps, dSubs, in->S, Sp, in->C, in->Ppad, TP,
-                                                      in->logScalers ? 1 : 0, stage);
+                                                      in->logScalers ? 1 : 0, stage, preOrder ? 1 : 0);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge derivatives (pre-order route): one block per edge, thread per pattern
+// ---------------------------------------------------------------------------------------------
+// d[e,p] = (sum_c w_c sum_j pre[c,p,j] (D_c post)[c,p,j]) / (sum_c w_c sum_j pre[c,p,j] post[c,p,j])
+// (preorder/AbstractBeagleBranchGradientDelegate.java:97-150 states the same reduction in Java).
+__global__ void __launch_bounds__(256)
+k_edge_derivatives(const EdgeRef* __restrict__ edges, const double* __restrict__ weights,
+                   const double* __restrict__ patternWeights, int S, int Sp, int C, int P, int Ppad, int matCP,
+                   int stageD, double* __restrict__ outPerPattern, double* __restrict__ outSum,
+                   double* __restrict__ outSumSq) {
+    extern __shared__ double smd[];            // D_c[j][k] row-major for all categories (when it fits)
+    __shared__ double red1[256], red2[256];
+    const EdgeRef e = edges[blockIdx.x];
+    const int tid = threadIdx.x;
+    auto dIndex = [&](int c, int j, int k) -> size_t {       // location of D[c][j][k] in the engine's matrix layouts
+        return matCP ? ((size_t)k * matCP + c) * 4 + j : ((size_t)c * Sp + k) * Sp + j;
+    };
+    if (stageD) {
+        for (int q = tid; q < C * S * S; q += 256) {
+            const int c = q / (S * S), r = q % (S * S);
+            smd[q] = e.D[dIndex(c, r / S, r % S)];
+        }
+        __syncthreads();
+    }
+    double acc1 = 0.0, acc2 = 0.0;
+    for (int p = tid; p < P; p += 256) {
+        double num = 0.0, den = 0.0;
+        const int s = e.states ? e.states[p] : -1;
+        for (int c = 0; c < C; ++c) {
+            const double* pre = e.pre + ((size_t)c * Ppad + p) * Sp;
+            const double* post = e.post ? e.post + ((size_t)c * Ppad + p) * Sp : nullptr;
+            double nc = 0.0, dc = 0.0;
+            for (int j = 0; j < S; ++j) {
+                double dp = 0.0, pj;
+                if (post) {
+                    for (int k2 = 0; k2 < S; ++k2)
+                        dp += (stageD ? smd[((size_t)c * S + j) * S + k2] : e.D[dIndex(c, j, k2)]) * post[k2];
+                    pj = post[j];
+                } else if (s < S) {
+                    dp = stageD ? smd[((size_t)c * S + j) * S + s] : e.D[dIndex(c, j, s)];
+                    pj = (j == s) ? 1.0 : 0.0;
+                } else {
+                    for (int k2 = 0; k2 < S; ++k2) dp += stageD ? smd[((size_t)c * S + j) * S + k2] : e.D[dIndex(c, j, k2)];
+                    pj = 1.0;
+                }
+                nc += pre[j] * dp;
+                dc += pre[j] * pj;
+            }
+            num += weights[c] * nc;
+            den += weights[c] * dc;
+        }
+        const double d = num / den;
+        if (outPerPattern) outPerPattern[(size_t)blockIdx.x * P + p] = d;
+        acc1 += patternWeights[p] * d;
+        acc2 += patternWeights[p] * d * d;
+    }
+    red1[tid] = acc1; red2[tid] = acc2;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) { red1[tid] += red1[tid + w]; red2[tid] += red2[tid + w]; }
+        __syncthreads();
+    }
+    if (tid == 0) { outSum[blockIdx.x] = red1[0]; outSumSq[blockIdx.x] = red2[0]; }
+}
+
+cudaError_t launchEdgeDerivatives(Instance* in, const EdgeRef* dEdges, int count, const double* weights,
+                                  double* outPerPattern, double* outSum, double* outSumSq) {
+    const size_t need = (size_t)in->C * in->S * in->S * sizeof(double);
+    const size_t budget = in->maxSmemOptin > 16384 ? in->maxSmemOptin - 8192 : 40000;
+    const int stageD = need <= budget ? 1 : 0;
+    const size_t smem = stageD ? need : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_edge_derivatives, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_edge_derivatives<<<count, 256, smem, in->stream>>>(dEdges, weights, in->dPatternWeights, in->S, in->Sp, in->C,
+                                                         in->P, in->Ppad, in->matCP, stageD, outPerPattern, outSum, outSumSq);
     return cudaGetLastError();
 }
 

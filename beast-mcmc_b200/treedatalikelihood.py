@@ -164,7 +164,7 @@ class BeagleDataLikelihoodDelegate:
                  rescalingScheme: str = PartialsRescalingScheme.DEFAULT,
                  delayRescalingUntilUnderflow: bool = True, resourceList=None,
                  preferenceFlags: int = 0, requirementFlags: int = 0,
-                 rescalingFrequency: int = RESCALE_FREQUENCY, stateSetFn=None):
+                 rescalingFrequency: int = RESCALE_FREQUENCY, stateSetFn=None, usePreOrder: bool = False):
         self.patternList = patternList
         self.patternCount = patternList.patternCount
         self.stateCount = patternList.stateCount
@@ -192,6 +192,11 @@ class BeagleDataLikelihoodDelegate:
         numPartials = self.partialBufferHelper.getBufferCount()
         numScaleBuffers = self.scaleBufferHelper.getBufferCount()
         numMatrices = self.evolutionaryProcessDelegate.getMatrixBufferCount()
+        self.usePreOrder = usePreOrder
+        if usePreOrder:        # BDLD:239-244: one pre-order partial per node, cached infinitesimal matrices
+            numPartials += self.nodeCount
+            numScaleBuffers += self.nodeCount - 1
+            numMatrices += 2 * self.evolutionaryProcessDelegate.getEigenBufferCount()
 
         self.rescalingScheme = rescalingScheme
         self.delayRescalingUntilUnderflow = delayRescalingUntilUnderflow
@@ -389,6 +394,12 @@ class BeagleDataLikelihoodDelegate:
         self.updateRootFrequency = False
         return logL
 
+    def getPartialBufferCount(self) -> int:
+        return self.partialBufferHelper.getBufferCount()
+
+    def getPartialBufferIndex(self, nodeNumber: int) -> int:
+        return self.partialBufferHelper.getOffsetIndex(nodeNumber)
+
     def getSiteLogLikelihoods(self) -> np.ndarray:
         out = np.zeros(self.patternCount)
         self.beagle.getSiteLogLikelihoods(out)
@@ -547,3 +558,71 @@ class TreeDataLikelihood:
         self.likelihoodDelegate.restoreState()
         self.logLikelihood = self._storedLogL
         self.likelihoodKnown = self._storedKnown
+
+
+class DiscreteTraitBranchRateDelegate:
+    """Re-enactment of the pre-order / branch-gradient route:
+    preorder/AbstractBeagleGradientDelegate.java:108-149,206-233 (simulateRoot, vectorizeNodeOperations,
+    updatePrePartials), preorder/AbstractBeagleBranchGradientDelegate.java:57-96 (calculateEdgeDifferentials),
+    discrete/DiscreteTraitBranchRateDelegate.java:49-89 (rate-scaled infinitesimal matrix),
+    SimulationTreeTraversal.java:78-122 (pre-order op list) and
+    HomogenousSubstitutionModelDelegate.java:140-147 (differential matrix buffer index).
+    getGradient() returns d logL / d (branch length) for every non-root node, in node-number order."""
+
+    def __init__(self, tree: Tree, likelihoodDelegate: BeagleDataLikelihoodDelegate, substitutionModel: SubstitutionModel):
+        assert likelihoodDelegate.usePreOrder
+        self.tree = tree
+        self.likelihoodDelegate = likelihoodDelegate
+        self.beagle = likelihoodDelegate.beagle
+        self.substitutionModel = substitutionModel
+        self.siteRateModel = likelihoodDelegate.siteRateModel
+        self.preOrderPartialOffset = likelihoodDelegate.getPartialBufferCount()
+        epd = likelihoodDelegate.evolutionaryProcessDelegate
+        self.firstDerivativeMatrixIndex = epd.getMatrixBufferCount() + epd.getEigenIndex(0)
+
+    def getPreOrderPartialIndex(self, node: int) -> int:
+        return self.preOrderPartialOffset + node
+
+    def _preOrderOperations(self):
+        tree, ops = self.tree, []
+        stack = [(tree.root, -1, -1)]
+        while stack:
+            node, parent, sibling = stack.pop()
+            if parent >= 0:
+                ops.append((parent, node, sibling))
+            if not tree.isExternal(node):
+                c1, c2 = int(tree.child[node][0]), int(tree.child[node][1])
+                stack.append((c2, node, c1))
+                stack.append((c1, node, c2))
+        return ops
+
+    def simulate(self) -> None:
+        d, b, tree = self.likelihoodDelegate, self.beagle, self.tree
+        P, S, C = d.patternCount, d.stateCount, d.categoryCount
+        freqs = np.asarray(d.evolutionaryProcessDelegate.getRootStateFrequencies(), dtype=np.float64)
+        b.setPartials(self.getPreOrderPartialIndex(tree.root), np.tile(freqs, P * C))        # simulateRoot
+        epd = d.evolutionaryProcessDelegate
+        ops = []
+        for parent, node, sibling in self._preOrderOperations():
+            ops += [self.getPreOrderPartialIndex(node), NONE, NONE, self.getPreOrderPartialIndex(parent),
+                    epd.getMatrixIndex(node), d.getPartialBufferIndex(sibling), epd.getMatrixIndex(sibling)]
+        b.updatePrePartials(np.asarray(ops, dtype=np.int32), len(ops) // 7, NONE)
+
+    def cacheDifferentialMassMatrix(self) -> None:
+        q = self.substitutionModel.infinitesimalMatrix().reshape(-1)
+        rates = self.siteRateModel.getCategoryRates()
+        scaled = np.concatenate([q * r for r in rates])
+        self.beagle.setDifferentialMatrix(self.firstDerivativeMatrixIndex, scaled)
+
+    def getGradient(self) -> np.ndarray:
+        tree, d = self.tree, self.likelihoodDelegate
+        self.simulate()
+        self.cacheDifferentialMassMatrix()
+        nodes = [n for n in range(tree.nodeCount) if n != tree.root]
+        post = np.asarray([d.getPartialBufferIndex(n) for n in nodes], dtype=np.int32)
+        pre = np.asarray([self.getPreOrderPartialIndex(n) for n in nodes], dtype=np.int32)
+        der = np.full(len(nodes), self.firstDerivativeMatrixIndex, dtype=np.int32)
+        first, firstSquared = np.zeros(len(nodes)), np.zeros(len(nodes))
+        self.beagle.calculateEdgeDifferentials(post, pre, der, np.zeros(1, dtype=np.int32), len(nodes), None,
+                                               first, firstSquared)
+        return first

@@ -220,6 +220,8 @@ BEAGLE_DLLEXPORT int beagleUpdateTransitionMatricesWithMultipleModels(
 BEAGLE_DLLEXPORT int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMatrix,
                                                double paddedValue);
 BEAGLE_DLLEXPORT int beagleGetTransitionMatrix(int instance, int matrixIndex, double* outMatrix);
+/* Beagle.setDifferentialMatrix(idx, double[C*S*S]) (HomogenousSubstitutionModelDelegate.java:160-176): same storage as a
+ * transition matrix; consumed by beagleCalculateEdgeDerivatives */
 BEAGLE_DLLEXPORT int beagleSetDifferentialMatrix(int instance, int matrixIndex, const double* inMatrix);
 /* SubstitutionModelDelegate.java:303-470 (epoch models) */
 BEAGLE_DLLEXPORT int beagleConvolveTransitionMatrices(int instance, const int* firstIndices,
@@ -242,7 +244,9 @@ BEAGLE_DLLEXPORT int beagleUpdatePartialsByPartition(int instance, const BeagleO
                                                      int operationCount);
 BEAGLE_DLLEXPORT int beagleWaitForPartials(int instance, const int* destinationPartials,
                                            int destinationPartialsCount);
-/* pre-order API: SURVEY.md 8f "next" row; returns BEAGLE_ERROR_NO_IMPLEMENTATION this round */
+/* Beagle.updatePrePartials(int[7n], n, cumulativeScaleIndex) (preorder/AbstractBeagleGradientDelegate.java:120,206-220):
+ * op = {pre[node], scaleWrite, scaleRead, pre[parent], matrix(node), post[sibling], matrix(sibling)};
+ * pre[node][c,p,j] = sum_i ( pre[parent][c,p,i] * sum_k M_sib[c,i,k] post[sib][c,p,k] ) * M_node[c,i,j]. */
 BEAGLE_DLLEXPORT int beagleUpdatePrePartials(int instance, const BeagleOperation* operations, int operationCount,
                                              int cumulativeScaleIndex);
 BEAGLE_DLLEXPORT int beagleUpdatePrePartialsByPartition(int instance, const BeagleOperationByPartition* operations,
@@ -279,6 +283,15 @@ BEAGLE_DLLEXPORT int beagleCalculateRootLogLikelihoodsByPartition(
     int instance, const int* bufferIndices, const int* categoryWeightsIndices, const int* stateFrequenciesIndices,
     const int* cumulativeScaleIndices, const int* partitionIndices, int partitionCount, int count,
     double* outSumLogLikelihoodByPartition, double* outSumLogLikelihood);
+/* Beagle.calculateEdgeDifferentials(post[], pre[], derivativeMatrix[], {weightsIdx}, count, out, outSum, outSumSquared)
+ * (preorder/AbstractBeagleBranchGradientDelegate.java:83-91): per edge e and pattern p
+ *   d[e,p] = (sum_c w_c sum_j pre[c,p,j] sum_k D[c,j,k] post[c,p,k]) / (sum_c w_c sum_j pre[c,p,j] post[c,p,j]);
+ * outDerivatives[e*P + p] = d (may be NULL), outSum[e] = sum_p weight_p d, outSumSquared[e] = sum_p weight_p d^2
+ * (each may be NULL).  D is a matrix buffer filled by beagleSetDifferentialMatrix. */
+BEAGLE_DLLEXPORT int beagleCalculateEdgeDerivatives(int instance, const int* postBufferIndices, const int* preBufferIndices,
+                                                    const int* derivativeMatrixIndices, const int* categoryWeightsIndices,
+                                                    int count, double* outDerivatives, double* outSumDerivatives,
+                                                    double* outSumSquaredDerivatives);
 /* Beagle.getSiteLogLikelihoods(double[P]) (BDLD:1020-1024; BTL:1050-1056) */
 BEAGLE_DLLEXPORT int beagleGetSiteLogLikelihoods(int instance, double* outLogLikelihoods);
 

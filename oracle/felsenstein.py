@@ -232,6 +232,73 @@ class OracleBeagle:
     def waitForPartials(self, destinationPartials, count):
         pass
 
+    # ---- pre-order partials and edge derivatives ---------------------------------
+    # Semantics recovered from the reference's call sites: op tuple = {pre[node], NONE, NONE, pre[parent],
+    # matrix(node), post[sibling], matrix(sibling)} (preorder/AbstractBeagleGradientDelegate.java:206-220),
+    # root pre-partial = frequencies (:139-149), and the defining identity the reference's own debug code
+    # states (preorder/AbstractBeagleBranchGradientDelegate.java:97-150):
+    #   site likelihood = sum_c w_c sum_j pre[node][c,p,j] * post[node][c,p,j]   for EVERY node.
+    def setDifferentialMatrix(self, matrixIndex, inMatrix):
+        self.setTransitionMatrix(matrixIndex, inMatrix)
+
+    def transposeTransitionMatrices(self, inputIndices, resultIndices, count):
+        for k in range(count):
+            self.matrices[resultIndices[k]] = np.transpose(self.matrices[inputIndices[k]], (0, 2, 1)).copy()
+
+    def updatePrePartials(self, operations, operationCount, cumulativeScaleIndex):
+        ops = np.asarray(operations, dtype=np.int64).reshape(-1)
+        sel = slice(None)
+        for k in range(operationCount):
+            dest, sw, sr, parentPre, m1, sib, m2 = ops[7 * k: 7 * k + 7]
+            q = self.partials[parentPre] * self._child_term(sib, m2, sel)        # at the parent: [C][P][S(i)]
+            M1 = self.matrices[m1]                                              # [C][i][j]
+            out = np.zeros_like(q)
+            for i in range(self.S):                                             # down the branch: sum_i q_i M[i][j]
+                out += q[:, :, i][:, :, None] * M1[:, None, i, :]
+            self.partials[dest] = out
+            self.tipStates[dest] = None
+            if sw >= 0:
+                self._rescale(dest, sel, sw, cumulativeScaleIndex)
+            elif sr >= 0:
+                f = self.scale[sr]
+                f = np.exp(f) if self.log_scalers else f
+                self.partials[dest] /= f[None, :, None]
+
+    def _post_as_partials(self, idx):
+        if self.tipStates[idx] is not None:
+            st = self.tipStates[idx]
+            out = np.ones((self.C, self.P, self.S))
+            known = st < self.S
+            onehot = np.zeros((self.P, self.S))
+            onehot[np.nonzero(known)[0], st[known]] = 1.0
+            out[:, known, :] = onehot[known][None, :, :]
+            return out
+        return self.partials[idx]
+
+    def calculateEdgeDifferentials(self, postBufferIndices, preBufferIndices, derivativeMatrixIndices,
+                                   categoryWeightsIndices, count, outDerivatives, outSumDerivatives,
+                                   outSumSquaredDerivatives):
+        w = self.categoryWeights[categoryWeightsIndices[0]]
+        for e in range(count):
+            post = self._post_as_partials(postBufferIndices[e])
+            pre = self.partials[preBufferIndices[e]]
+            D = self.matrices[derivativeMatrixIndices[e]]                       # [C][j][k]
+            num = np.zeros(self.P)
+            den = np.zeros(self.P)
+            for c in range(self.C):
+                Dpost = np.zeros((self.P, self.S))
+                for k in range(self.S):
+                    Dpost += D[c][None, :, k] * post[c][:, k][:, None]
+                num += w[c] * (pre[c] * Dpost).sum(axis=1)
+                den += w[c] * (pre[c] * post[c]).sum(axis=1)
+            d = num / den
+            if outDerivatives is not None:
+                outDerivatives[e * self.P:(e + 1) * self.P] = d
+            if outSumDerivatives is not None:
+                outSumDerivatives[e] = float(np.dot(self.patternWeights, d))
+            if outSumSquaredDerivatives is not None:
+                outSumSquaredDerivatives[e] = float(np.dot(self.patternWeights, d * d))
+
     # ---- scale factors ------------------------------------------------------------------
     def _logf(self, idx):
         return self.scale[idx] if self.log_scalers else np.log(self.scale[idx])
