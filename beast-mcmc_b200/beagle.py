@@ -333,6 +333,20 @@ class BeagleJNIImpl(Beagle):
         self._check("transposeTransitionMatrices",
                     self._lib.beagleTransposeTransitionMatrices(self.instance, _ip(inputIndices)[1], _ip(resultIndices)[1], matrixCount))
 
+    def convolveTransitionMatrices(self, firstIndices, secondIndices, resultIndices, matrixCount):
+        self._check("convolveTransitionMatrices",
+                    self._lib.beagleConvolveTransitionMatrices(self.instance, _ip(firstIndices)[1], _ip(secondIndices)[1],
+                                                               _ip(resultIndices)[1], matrixCount))
+
+    def addTransitionMatrices(self, firstIndices, secondIndices, resultIndices, matrixCount):
+        self._check("addTransitionMatrices",
+                    self._lib.beagleAddTransitionMatrices(self.instance, _ip(firstIndices)[1], _ip(secondIndices)[1],
+                                                          _ip(resultIndices)[1], matrixCount))
+
+    def updatePrePartialsByPartition(self, operations, operationCount):
+        self._check("updatePrePartialsByPartition",
+                    self._lib.beagleUpdatePrePartialsByPartition(self.instance, _ip(operations)[1], operationCount))
+
     def updatePrePartials(self, operations, operationCount, cumulativeScaleIndex):
         self._check("updatePrePartials", self._lib.beagleUpdatePrePartials(self.instance, _ip(operations)[1],
                                                                            operationCount, cumulativeScaleIndex))

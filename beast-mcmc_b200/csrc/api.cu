@@ -28,7 +28,8 @@ const long kSupportedFlags =
     BEAGLE_FLAG_PRECISION_DOUBLE | BEAGLE_FLAG_COMPUTATION_SYNCH | BEAGLE_FLAG_EIGEN_REAL |
     BEAGLE_FLAG_EIGEN_COMPLEX | BEAGLE_FLAG_SCALING_MANUAL | BEAGLE_FLAG_SCALING_DYNAMIC |
     BEAGLE_FLAG_SCALERS_RAW | BEAGLE_FLAG_SCALERS_LOG | BEAGLE_FLAG_VECTOR_NONE | BEAGLE_FLAG_THREADING_NONE |
-    BEAGLE_FLAG_PROCESSOR_GPU | BEAGLE_FLAG_FRAMEWORK_CUDA | BEAGLE_FLAG_PARALLELOPS_GRID;
+    BEAGLE_FLAG_PROCESSOR_GPU | BEAGLE_FLAG_FRAMEWORK_CUDA | BEAGLE_FLAG_PARALLELOPS_GRID |
+    BEAGLE_FLAG_PREORDER_TRANSPOSE_AUTO;     // updatePrePartials always applies the node matrix transposed itself
 
 int envInt(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -201,7 +202,7 @@ struct Plan {
 };
 
 void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder, int fixedT, int wantSubs, int minT,
-                Plan& plan) {
+                int smallRemainder, Plan& plan) {
     const int n = (int)ops.size();
     auto single = [&]() {
         plan.order.resize(n);
@@ -231,7 +232,7 @@ void planPhases(const std::vector<HostOp>& ops, int nBuffers, bool allowReorder,
     while (remaining > 0) {
         // per-phase subtree bound: enough subtrees to fill the machine, re-evaluated on what is left
         // (a remainder of a couple of dozen ops is cheaper as one launch than as several tiny phases)
-        const int T = fixedT > 0 ? fixedT : (remaining <= 24 ? remaining : std::max(minT, (remaining + wantSubs - 1) / wantSubs));
+        const int T = fixedT > 0 ? fixedT : (remaining <= smallRemainder ? remaining : std::max(minT, (remaining + wantSubs - 1) / wantSubs));
         for (int k = 0; k < n; ++k) {
             if (!alive[k]) continue;
             const int a = (ch0[k] >= 0 && alive[ch0[k]]) ? ch0[k] : -1;
@@ -336,7 +337,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         };
         if (!byPartition) {
             if (hops[0].kind == 1) planLevels(hops, in->nBuffers, plan);
-            else planPhases(hops, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(in->Ppad), in->phaseTmin, plan);
+            else planPhases(hops, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(in->Ppad), in->phaseTmin, in->phaseSmall, plan);
             for (Sub& sb : plan.subs) { sb.pBase = 0; sb.pLimit = in->Ppad; }
         } else {
             // partitions are independent (disjoint pattern windows): plan each one on its own and merge the
@@ -352,7 +353,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
                 for (size_t q = 0; q < sub.size(); ++q) sub[q] = hops[members[part][q]];
                 Plan pl;
                 const int window = in->partEnd[part] - in->partBegin[part];
-                planPhases(sub, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(std::max(1, window)), in->phaseTmin, pl);
+                if (sub[0].kind == 1) planLevels(sub, in->nBuffers, pl);
+                else planPhases(sub, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(std::max(1, window)), in->phaseTmin, in->phaseSmall, pl);
                 base.push_back((int)plan.order.size());
                 for (int idx : pl.order) plan.order.push_back(members[part][idx]);
                 for (Sub& sb : pl.subs) {
@@ -556,6 +558,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
                 BEAGLE_FLAG_FRAMEWORK_CUDA | BEAGLE_FLAG_PARALLELOPS_GRID |
                 (in->complexEigen ? BEAGLE_FLAG_EIGEN_COMPLEX : BEAGLE_FLAG_EIGEN_REAL) |
                 (in->logScalers ? BEAGLE_FLAG_SCALERS_LOG : BEAGLE_FLAG_SCALERS_RAW);
+    if ((requirementFlags | preferenceFlags) & BEAGLE_FLAG_PREORDER_TRANSPOSE_AUTO) in->flags |= BEAGLE_FLAG_PREORDER_TRANSPOSE_AUTO;
     if ((requirementFlags | preferenceFlags) & BEAGLE_FLAG_SCALING_DYNAMIC) {
         in->flags &= ~BEAGLE_FLAG_SCALING_MANUAL;
         in->flags |= BEAGLE_FLAG_SCALING_DYNAMIC;
@@ -579,11 +582,18 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->reorder = envInt("B200_REORDER", 1);
     in->phaseT = envInt("B200_PHASE_T", 0);
     in->phaseTmin = std::max(1, envInt("B200_PHASE_TMIN", 4));
+    in->phaseSmall = envInt("B200_PHASE_SMALL", 24);
     in->phaseOversub = std::max(1, envInt("B200_PHASE_OVERSUB", 2));
     in->walkMinBlocks = envInt("B200_WALK_MINB", 4);
     in->genericMma = envInt("B200_GENERIC_MMA", 1);
+    in->mmaWarps = envInt("B200_MMA_WARPS", 4) == 8 ? 8 : 4;     // 8 = 256-thread blocks with cp.async double buffering
     in->walkR = envInt("B200_WALK_R", 4);
-    if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4) in->walkR = 2;
+    if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4) in->walkR = 4;
+    if (getenv("B200_WALK_R") == nullptr && in->matCP > 0) {
+        // patterns per thread: as many as still leave >= 2 warps per SM inside ONE subtree walk
+        const int G = 32 / in->matCP;
+        while (in->walkR > 1 && (in->Ppad + G * in->walkR - 1) / (G * in->walkR) < 2 * in->smCount) in->walkR >>= 1;
+    }
     in->stackDepthMax = std::min(64, std::max(0, envInt("B200_STACK_DEPTH", 12)));
 
     cudaDeviceProp prop;
@@ -936,8 +946,45 @@ int beagleGetTransitionMatrix(int instance, int matrixIndex, double* outMatrix) 
 int beagleSetDifferentialMatrix(int instance, int matrixIndex, const double* inMatrix) {
     return beagleSetTransitionMatrix(instance, matrixIndex, inMatrix, 0.0);     // same storage, all layouts
 }
-int beagleConvolveTransitionMatrices(int, const int*, const int*, const int*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
-int beagleAddTransitionMatrices(int, const int*, const int*, const int*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+// SubstitutionModelDelegate.java:303-470 (epoch / branch-specific models): result = first x second per category,
+// resp. first + second.  A handful of S x S products per call: done on the host between a get and a set.
+static int combineMatrices(int instance, const int* firstIndices, const int* secondIndices, const int* resultIndices,
+                           int matrixCount, bool multiply) {
+    GET_INSTANCE(in, instance);
+    const size_t n = (size_t)in->C * in->S * in->S;
+    std::vector<double> a(n), b(n), r(n);
+    for (int q = 0; q < matrixCount; ++q) {
+        int rc = beagleGetTransitionMatrix(instance, firstIndices[q], a.data());
+        if (rc == BEAGLE_SUCCESS) rc = beagleGetTransitionMatrix(instance, secondIndices[q], b.data());
+        if (rc != BEAGLE_SUCCESS) return rc;
+        const int S = in->S;
+        for (int c = 0; c < in->C; ++c) {
+            const double* A = a.data() + (size_t)c * S * S;
+            const double* B = b.data() + (size_t)c * S * S;
+            double* R = r.data() + (size_t)c * S * S;
+            for (int i = 0; i < S; ++i)
+                for (int j = 0; j < S; ++j) {
+                    double v = 0.0;
+                    if (multiply) for (int k = 0; k < S; ++k) v += A[i * S + k] * B[k * S + j];
+                    else v = A[i * S + j] + B[i * S + j];
+                    R[i * S + j] = v;
+                }
+        }
+        rc = beagleSetTransitionMatrix(instance, resultIndices[q], r.data(), 0.0);
+        if (rc != BEAGLE_SUCCESS) return rc;
+    }
+    return BEAGLE_SUCCESS;
+}
+
+int beagleConvolveTransitionMatrices(int instance, const int* firstIndices, const int* secondIndices,
+                                     const int* resultIndices, int matrixCount) {
+    return combineMatrices(instance, firstIndices, secondIndices, resultIndices, matrixCount, true);
+}
+
+int beagleAddTransitionMatrices(int instance, const int* firstIndices, const int* secondIndices, const int* resultIndices,
+                                int matrixCount) {
+    return combineMatrices(instance, firstIndices, secondIndices, resultIndices, matrixCount, false);
+}
 int beagleTransposeTransitionMatrices(int instance, const int* inputIndices, const int* resultIndices, int matrixCount) {
     GET_INSTANCE(in, instance);
     std::vector<double> m((size_t)in->C * in->S * in->S), t(m.size());
@@ -999,7 +1046,19 @@ int beagleUpdatePrePartials(int instance, const BeagleOperation* operations, int
     }
     return planAndLaunch(in, hops, false);
 }
-int beagleUpdatePrePartialsByPartition(int, const BeagleOperationByPartition*, int) { return BEAGLE_ERROR_NO_IMPLEMENTATION; }
+int beagleUpdatePrePartialsByPartition(int instance, const BeagleOperationByPartition* operations, int operationCount) {
+    GET_INSTANCE(in, instance);
+    if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<HostOp> hops(operationCount);
+    for (int k = 0; k < operationCount; ++k) {
+        const BeagleOperationByPartition& o = operations[k];
+        hops[k] = {o.destinationPartials, o.destinationScaleWrite, o.destinationScaleRead, o.child1Partials,
+                   o.child1TransitionMatrix, o.child2Partials, o.child2TransitionMatrix, o.partition,
+                   o.cumulativeScaleIndex};
+        hops[k].kind = 1;
+    }
+    return planAndLaunch(in, hops, true);
+}
 
 // ---- scale factors ----------------------------------------------------------------------------
 static int accumulateImpl(Instance* in, const int* scaleIndices, int count, int cum, double sign, int pBegin, int pEnd) {

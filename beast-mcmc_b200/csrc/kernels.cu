@@ -310,7 +310,7 @@ __device__ __forceinline__ void childTerm(const WalkArgs& A, int child, int matI
     }
 }
 
-template <int CP, int R, bool STACK, int MINB>
+template <int CP, int R, bool STACK, int MINB, bool PRE>
 __global__ void __launch_bounds__(128, MINB)
 k_walk4(const WalkArgs A) {
     constexpr int G = 32 / CP;
@@ -334,7 +334,7 @@ k_walk4(const WalkArgs A) {
         const Op4 nxt = loadOp(A.ops + min(k + 1, last));      // one record ahead, off the dependent chain
         const int s1 = cur.slots & 0xFF, s2 = (cur.slots >> 8) & 0xFF, sd = (cur.slots >> 16) & 0xFF;
         double d[R][4];
-        if (cur.pad_ == 0) {
+        if (!PRE) {
             childTerm<CP, R, STACK, true>(A, cur.c1, cur.m1, s1, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
             childTerm<CP, R, STACK, false>(A, cur.c2, cur.m2, s2, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
         } else {
@@ -393,19 +393,19 @@ k_walk4(const WalkArgs A) {
     }
 }
 
-template <int CP, int R, bool STACK, int MINB>
+template <int CP, int R, bool STACK, int MINB, bool PRE = false>
 static cudaError_t launchWalk4K(Instance* in, const WalkArgs& A, dim3 grid, size_t smem) {
     if (smem > 0 && smem > in->walkSmemConfigured) {
-        cudaError_t e = cudaFuncSetAttribute(k_walk4<CP, R, STACK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_walk4<CP, R, STACK, MINB, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         in->walkSmemConfigured = smem;
     }
-    k_walk4<CP, R, STACK, MINB><<<grid, 128, smem, in->stream>>>(A);
+    k_walk4<CP, R, STACK, MINB, PRE><<<grid, 128, smem, in->stream>>>(A);
     return cudaGetLastError();
 }
 
 template <int CP, int R>
-static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow) {
+static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder) {
     constexpr int G = 32 / CP;
     const int warps = (maxWindow + G * R - 1) / (G * R);
     dim3 grid((warps + 3) / 4, nSubs);
@@ -414,6 +414,7 @@ static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int4* dSubs
     A.states = in->states8Base; A.mats = in->dMat; A.scale = in->dScale;
     A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.logScalers = in->logScalers ? 1 : 0;
     A.matStride = in->matStride; A.matMmaOffset = 16 * in->matCP;
+    if (preOrder) return launchWalk4K<CP, R, false, 4, true>(in, A, grid, 0);
     if (stackDepth > 0) return launchWalk4K<CP, R, true, 4>(in, A, grid, (size_t)stackDepth * 32 * R * 128);
     if (in->walkMinBlocks >= 6) return launchWalk4K<CP, R, false, 6>(in, A, grid, 0);
     if (in->walkMinBlocks == 5) return launchWalk4K<CP, R, false, 5>(in, A, grid, 0);
@@ -581,11 +582,11 @@ static cudaError_t launchWalk4Mma(Instance* in, const Op4* dOps, const int4* dSu
 }
 
 template <int CP>
-static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow) {
+static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder) {
     switch (in->walkR) {
-        case 4: return launchWalk4R<CP, 4>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
-        case 2: return launchWalk4R<CP, 2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
-        default: return launchWalk4R<CP, 1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        case 4: return launchWalk4R<CP, 4>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
+        case 2: return launchWalk4R<CP, 2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
+        default: return launchWalk4R<CP, 1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
     }
 }
 
@@ -593,12 +594,12 @@ cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nS
     if (nSubs <= 0) return cudaSuccess;
     if (in->walkVariant == 2 && !preOrder) return launchWalk4Mma(in, dOps, dSubs, nSubs, maxWindow);
     switch (in->matCP) {
-        case 1: return launchWalk4T<1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
-        case 2: return launchWalk4T<2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
-        case 4: return launchWalk4T<4>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
-        case 8: return launchWalk4T<8>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
-        case 16: return launchWalk4T<16>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
-        default: return launchWalk4T<32>(in, dOps, dSubs, nSubs, stackDepth, maxWindow);
+        case 1: return launchWalk4T<1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
+        case 2: return launchWalk4T<2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
+        case 4: return launchWalk4T<4>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
+        case 8: return launchWalk4T<8>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
+        case 16: return launchWalk4T<16>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
+        default: return launchWalk4T<32>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
     }
 }
 
@@ -748,106 +749,134 @@ k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int
 // shared memory with a (Sp+4)-double row stride (conflict-free for the 8x4 fragment shape), and the
 // 16 x Sp accumulator tile of each warp lives in registers.  Block = 4 warps x 16 patterns.
 
-template <int NT>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmemSrc) : "memory");
+}
+
+// Block = WARPS warps x 16 patterns.  The two matrices of the NEXT (op, category) pair are fetched with
+// cp.async (LDGSTS) into the other half of a double buffer while the tensor pipe works on the current pair.
+template <int NT, int WARPS, bool DB>
+__global__ void __launch_bounds__(WARPS * 32)
 k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int C, int Ppad, int logScalers) {
     constexpr int Sp = 8 * NT;
     constexpr int LD = Sp + 4;                       // shared-memory row stride (doubles)
-    extern __shared__ double smm[];
-    double* P1 = smm;
-    double* P2 = smm + Sp * LD;
+    constexpr int NTHREADS = WARPS * 32;
+    constexpr int MATSZ = Sp * LD;
+    extern __shared__ double smm[];                  // [2 buffers][2 matrices][Sp][LD]
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int4 range = subs[blockIdx.y];
-    if (range.z + blockIdx.x * 64 >= range.w) return;      // block outside this subtree's pattern window
-    const int pw = range.z + blockIdx.x * 64 + w * 16;     // first pattern of this warp's 16-row tile
+    if (range.z + blockIdx.x * (WARPS * 16) >= range.w) return;      // block outside this subtree's pattern window
+    const int pw = range.z + blockIdx.x * (WARPS * 16) + w * 16;      // first pattern of this warp's 16-row tile
     const size_t mRow = (size_t)C * Sp * Sp;         // offset of the row-major copies in a matrix buffer
+    const int total = (range.y - range.x) * C;
 
-    for (int k = range.x; k < range.y; ++k) {
-        const DevOp op = ops[k];
-        bool act[2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            const int p = pw + 8 * m + g;
-            act[m] = p < range.w && p >= op.pBegin && p < op.pEnd;
+    auto stageAsync = [&](int flat, int buf) {
+        const DevOp* o = ops + range.x + flat / C;
+        const int c = flat % C;
+        const double* g1 = o->m1 + mRow + (size_t)c * Sp * Sp;
+        const double* g2 = o->m2 + mRow + (size_t)c * Sp * Sp;
+        double* s1 = smm + (size_t)buf * 2 * MATSZ;
+        double* s2 = s1 + MATSZ;
+        for (int q = tid; q < Sp * Sp / 2; q += NTHREADS) {
+            const int i = (2 * q) / Sp, j = (2 * q) % Sp;
+            cpAsync16(s1 + i * LD + j, g1 + 2 * q);
+            cpAsync16(s2 + i * LD + j, g2 + 2 * q);
         }
-        double rowMax[2] = {0.0, 0.0};
-        for (int c = 0; c < C; ++c) {
-            __syncthreads();
-            {   // stage both row-major matrices: global [i][j] (stride Sp) -> shared [i][j] (stride LD)
-                const double* g1 = op.m1 + mRow + (size_t)c * Sp * Sp;
-                const double* g2 = op.m2 + mRow + (size_t)c * Sp * Sp;
-                for (int q = tid; q < Sp * Sp / 2; q += 128) {
-                    const int i = (2 * q) / Sp, j = (2 * q) % Sp;
-                    const double2 v1 = __ldg(reinterpret_cast<const double2*>(g1) + q);
-                    const double2 v2 = __ldg(reinterpret_cast<const double2*>(g2) + q);
-                    *reinterpret_cast<double2*>(P1 + i * LD + j) = v1;
-                    *reinterpret_cast<double2*>(P2 + i * LD + j) = v2;
-                }
+    };
+
+    if (DB) {
+        stageAsync(0, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    bool act[2] = {false, false};
+    double rowMax[2] = {0.0, 0.0};
+    for (int flat = 0; flat < total; ++flat) {
+        if (DB) {
+            if (flat + 1 < total) stageAsync(flat + 1, (flat + 1) & 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            // single buffer: more resident blocks per SM hide the staging instead (measured faster at Sp = 64)
+            stageAsync(flat, 0);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const DevOp op = ops[range.x + flat / C];
+        const int c = flat % C;
+        const double* P1 = smm + (size_t)(DB ? (flat & 1) : 0) * 2 * MATSZ;
+        const double* P2 = P1 + MATSZ;
+        if (c == 0) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int p = pw + 8 * m + g;
+                act[m] = p < range.w && p >= op.pBegin && p < op.pEnd;
+                rowMax[m] = 0.0;
             }
-            __syncthreads();
-            double acc[2][NT][2];
+        }
+        double acc[2][NT][2];
 #pragma unroll
-            for (int child = 0; child < 2; ++child) {
-                const double* xg = child == 0 ? op.c1 : op.c2;
-                const double* Ps = child == 0 ? P1 : P2;
-                double cur[2][NT][2];
-                if (xg != nullptr) {
-#pragma unroll
-                    for (int m = 0; m < 2; ++m)
-#pragma unroll
-                        for (int n = 0; n < NT; ++n) { cur[m][n][0] = 0.0; cur[m][n][1] = 0.0; }
-                    const double* xrow0 = xg + ((size_t)c * Ppad + (pw + g)) * Sp + t;
-                    const double* xrow1 = xrow0 + (size_t)8 * Sp;
-                    const double* brow = Ps + g * LD + t;
-#pragma unroll 4
-                    for (int kc = 0; kc < Sp / 4; ++kc) {
-                        double a0 = 0.0, a1 = 0.0;
-                        if (act[0]) a0 = xrow0[4 * kc];
-                        if (act[1]) a1 = xrow1[4 * kc];
-#pragma unroll
-                        for (int n = 0; n < NT; ++n) {
-                            const double b = brow[n * 8 * LD + 4 * kc];
-                            dmma884acc(cur[0][n][0], cur[0][n][1], a0, b);
-                            dmma884acc(cur[1][n][0], cur[1][n][1], a1, b);
-                        }
-                    }
-                } else {
-                    const int* st = static_cast<const int*>(child == 0 ? op.s1 : op.s2);
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) {
-                        const int p = pw + 8 * m + g;
-                        const int s = act[m] ? st[p] : S;
-#pragma unroll
-                        for (int n = 0; n < NT; ++n)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int i = 8 * n + 2 * t + e;
-                                cur[m][n][e] = (s < S) ? Ps[i * LD + s] : ((i < S) ? 1.0 : 0.0);
-                            }
-                    }
-                }
+        for (int child = 0; child < 2; ++child) {
+            const double* xg = child == 0 ? op.c1 : op.c2;
+            const double* Ps = child == 0 ? P1 : P2;
+            double cur[2][NT][2];
+            if (xg != nullptr) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m)
 #pragma unroll
+                    for (int n = 0; n < NT; ++n) { cur[m][n][0] = 0.0; cur[m][n][1] = 0.0; }
+                const double* xrow0 = xg + ((size_t)c * Ppad + (pw + g)) * Sp + t;
+                const double* xrow1 = xrow0 + (size_t)8 * Sp;
+                const double* brow = Ps + g * LD + t;
+#pragma unroll 4
+                for (int kc = 0; kc < Sp / 4; ++kc) {
+                    double a0 = 0.0, a1 = 0.0;
+                    if (act[0]) a0 = xrow0[4 * kc];
+                    if (act[1]) a1 = xrow1[4 * kc];
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        const double b = brow[n * 8 * LD + 4 * kc];
+                        dmma884acc(cur[0][n][0], cur[0][n][1], a0, b);
+                        dmma884acc(cur[1][n][0], cur[1][n][1], a1, b);
+                    }
+                }
+            } else {
+                const int* st = static_cast<const int*>(child == 0 ? op.s1 : op.s2);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int p = pw + 8 * m + g;
+                    const int s = act[m] ? st[p] : S;
+#pragma unroll
                     for (int n = 0; n < NT; ++n)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e)
-                            acc[m][n][e] = child == 0 ? cur[m][n][e] : acc[m][n][e] * cur[m][n][e];
-            }
-            // store the (unscaled) tile: lane (g,t) owns states 8n+2t, 8n+2t+1 of rows g and g+8
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                if (!act[m]) continue;
-                double* drow = op.dest + ((size_t)c * Ppad + (pw + 8 * m + g)) * Sp + 2 * t;
-#pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    *reinterpret_cast<double2*>(drow + 8 * n) = make_double2(acc[m][n][0], acc[m][n][1]);
-                    rowMax[m] = fmax(rowMax[m], fmax(acc[m][n][0], acc[m][n][1]));
+                        for (int e = 0; e < 2; ++e) {
+                            const int i = 8 * n + 2 * t + e;
+                            cur[m][n][e] = (s < S) ? Ps[i * LD + s] : ((i < S) ? 1.0 : 0.0);
+                        }
                 }
             }
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        acc[m][n][e] = child == 0 ? cur[m][n][e] : acc[m][n][e] * cur[m][n][e];
         }
-        if (op.scaleWrite != nullptr || op.scaleRead != nullptr) {
+        // store the (unscaled) tile: lane (g,t) owns states 8n+2t, 8n+2t+1 of rows g and g+8
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            if (!act[m]) continue;
+            double* drow = op.dest + ((size_t)c * Ppad + (pw + 8 * m + g)) * Sp + 2 * t;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                *reinterpret_cast<double2*>(drow + 8 * n) = make_double2(acc[m][n][0], acc[m][n][1]);
+                rowMax[m] = fmax(rowMax[m], fmax(acc[m][n][0], acc[m][n][1]));
+            }
+        }
+        if (c == C - 1 && (op.scaleWrite != nullptr || op.scaleRead != nullptr)) {
             // per-pattern factor (max over categories and states), then one more pass over what this
             // warp just wrote (same lanes re-read their own stores)
 #pragma unroll
@@ -871,8 +900,8 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 }
                 if (act[m]) {
                     const double inv = 1.0 / f;
-                    for (int c = 0; c < C; ++c) {
-                        double* drow = op.dest + ((size_t)c * Ppad + p) * Sp + 2 * t;
+                    for (int cc = 0; cc < C; ++cc) {
+                        double* drow = op.dest + ((size_t)cc * Ppad + p) * Sp + 2 * t;
 #pragma unroll
                         for (int n = 0; n < NT; ++n) {
                             double2 v = *reinterpret_cast<double2*>(drow + 8 * n);
@@ -883,22 +912,23 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 }
             }
         }
-        __syncthreads();      // children of the next op may have been written by other warps? no: rows are warp-private,
-                              // but the shared matrices are about to be overwritten
+        // (a) every warp is done with this buffer before the copy issued next iteration overwrites it,
+        // (b) rows written by other lanes of this warp become visible to the next op's A-fragment loads
+        __syncthreads();
     }
 }
 
-template <int NT>
+template <int NT, int WARPS, bool DB = false>
 static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     constexpr int Sp = 8 * NT;
-    const size_t smem = 2 * (size_t)Sp * (Sp + 4) * sizeof(double);
+    const size_t smem = (DB ? 4 : 2) * (size_t)Sp * (Sp + 4) * sizeof(double);
     if (smem > in->mmaSmemConfigured) {
-        cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         in->mmaSmemConfigured = smem;
     }
-    dim3 grid((maxWindow + 63) / 64, nSubs);
-    k_walk_mma<NT><<<grid, 128, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
+    dim3 grid((maxWindow + WARPS * 16 - 1) / (WARPS * 16), nSubs);
+    k_walk_mma<NT, WARPS, DB><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -906,11 +936,11 @@ cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs
     if (nSubs <= 0) return cudaSuccess;
     if (in->genericMma && !preOrder) {
         switch (in->Sp / 8) {
-            case 1: return launchWalkMmaT<1>(in, dOps, dSubs, nSubs, maxWindow);
-            case 2: return launchWalkMmaT<2>(in, dOps, dSubs, nSubs, maxWindow);
-            case 3: return launchWalkMmaT<3>(in, dOps, dSubs, nSubs, maxWindow);
-            case 4: return launchWalkMmaT<4>(in, dOps, dSubs, nSubs, maxWindow);
-            case 8: return launchWalkMmaT<8>(in, dOps, dSubs, nSubs, maxWindow);
+            case 1: return launchWalkMmaT<1, 4>(in, dOps, dSubs, nSubs, maxWindow);
+            case 2: return launchWalkMmaT<2, 4>(in, dOps, dSubs, nSubs, maxWindow);
+            case 3: return launchWalkMmaT<3, 4>(in, dOps, dSubs, nSubs, maxWindow);
+            case 4: return launchWalkMmaT<4, 4>(in, dOps, dSubs, nSubs, maxWindow);
+            case 8: return in->mmaWarps == 8 ? launchWalkMmaT<8, 8, true>(in, dOps, dSubs, nSubs, maxWindow) : launchWalkMmaT<8, 4>(in, dOps, dSubs, nSubs, maxWindow);
             default: break;      // other state counts: FMA block walk below
         }
     }

@@ -245,6 +245,16 @@ class OracleBeagle:
         for k in range(count):
             self.matrices[resultIndices[k]] = np.transpose(self.matrices[inputIndices[k]], (0, 2, 1)).copy()
 
+    def convolveTransitionMatrices(self, firstIndices, secondIndices, resultIndices, count):
+        # SubstitutionModelDelegate.java:303-470: P_result = P_first x P_second per category
+        for k in range(count):
+            self.matrices[resultIndices[k]] = np.einsum("cik,ckj->cij", self.matrices[firstIndices[k]],
+                                                        self.matrices[secondIndices[k]])
+
+    def addTransitionMatrices(self, firstIndices, secondIndices, resultIndices, count):
+        for k in range(count):
+            self.matrices[resultIndices[k]] = self.matrices[firstIndices[k]] + self.matrices[secondIndices[k]]
+
     def updatePrePartials(self, operations, operationCount, cumulativeScaleIndex):
         ops = np.asarray(operations, dtype=np.int64).reshape(-1)
         sel = slice(None)

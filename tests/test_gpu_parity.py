@@ -297,6 +297,30 @@ def test_transition_matrices_match_oracle_incl_complex():
     b.finalize()
 
 
+def test_matrix_convolution_and_addition():
+    """convolve/addTransitionMatrices (epoch models, SubstitutionModelDelegate.java:303-470): P(t1) x P(t2) == P(t1+t2)."""
+    tree, pats, model, site = H.synthetic_case(6, 40, 3, seed=2, stateCount=7)
+    S, C = 7, 3
+    b = GPU(6, 11, 6, S, pats.patternCount, 1, 8, C, 0, [1, 0], 0, 0)
+    o = H.oracle_factory()(6, 11, 6, S, pats.patternCount, 1, 8, C, 0, None, 0, 0)
+    e = model.getEigenDecomposition()
+    got = []
+    for inst in (b, o):
+        inst.setEigenDecomposition(0, e.Evec, e.Ievc, e.Eval)
+        inst.setCategoryRates(site.getCategoryRates())
+        inst.updateTransitionMatrices(0, np.array([0, 1, 2], dtype=np.int32), None, None, np.array([0.03, 0.07, 0.10]), 3)
+        inst.convolveTransitionMatrices(np.array([0], dtype=np.int32), np.array([1], dtype=np.int32), np.array([3], dtype=np.int32), 1)
+        inst.addTransitionMatrices(np.array([0], dtype=np.int32), np.array([1], dtype=np.int32), np.array([4], dtype=np.int32), 1)
+        m = [np.zeros(C * S * S) for _ in range(3)]
+        for k, idx in enumerate((2, 3, 4)):
+            inst.getTransitionMatrix(idx, m[k])
+        got.append(m)
+    assert np.allclose(got[0][1], got[0][0], rtol=1e-12, atol=1e-14)          # Chapman-Kolmogorov
+    for x, y in zip(got[0], got[1]):
+        assert np.allclose(x, y, rtol=1e-12, atol=1e-15)
+    b.finalize()
+
+
 def test_set_get_roundtrips_and_errors():
     b = GPU(4, 7, 4, 4, 37, 2, 14, 3, 8, [1, 0], 0, 0)
     rng = np.random.default_rng(2)
