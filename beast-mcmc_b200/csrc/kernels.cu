@@ -1111,25 +1111,38 @@ cudaError_t launchRoot(Instance* in, const double* root, const double* weights, 
 // ---------------------------------------------------------------------------------------------
 // scale-factor accumulation:  cum[p] += sign * sum_k log-factor_k[p]   (BDLD:915-926)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_scale_accum(const double* __restrict__ scaleBase, int Ppad, const int* __restrict__ idx,
-                              int count, double* __restrict__ cum, double sign, int logScalers, int pBegin,
-                              int pEnd) {
-    const int p = pBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pEnd) return;
+// block = 32 patterns x 16 buffer-lanes: lane j sums buffers j, j+16, ... (independent loads in flight), then a
+// fixed-order reduction over the 16 lanes -> deterministic, and N-1 buffers no longer serialise on one thread.
+__global__ void __launch_bounds__(512)
+k_scale_accum(const double* __restrict__ scaleBase, int Ppad, const int* __restrict__ idx,
+              int count, double* __restrict__ cum, double sign, int logScalers, int pBegin, int pEnd) {
+    __shared__ double part[16][33];
+    const int px = threadIdx.x, ky = threadIdx.y;
+    const int p = pBegin + blockIdx.x * 32 + px;
     double acc = 0.0;
-    for (int k = 0; k < count; ++k) {
-        double f = scaleBase[(size_t)idx[k] * Ppad + p];
-        acc += logScalers ? f : log(f);
+    if (p < pEnd) {
+#pragma unroll 4
+        for (int k = ky; k < count; k += 16) {
+            const double f = scaleBase[(size_t)idx[k] * Ppad + p];
+            acc += logScalers ? f : log(f);
+        }
     }
-    cum[p] += sign * acc;
+    part[ky][px] = acc;
+    __syncthreads();
+    if (ky == 0 && p < pEnd) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += part[j][px];
+        cum[p] += sign * s;
+    }
 }
 
 cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,
                                   int pBegin, int pEnd) {
     int n = pEnd - pBegin;
     if (n <= 0 || count <= 0) return cudaSuccess;
-    k_scale_accum<<<(n + 127) / 128, 128, 0, in->stream>>>(in->dScale, in->Ppad, dIdx, count, cum, sign,
-                                                           in->logScalers ? 1 : 0, pBegin, pEnd);
+    k_scale_accum<<<(n + 31) / 32, dim3(32, 16), 0, in->stream>>>(in->dScale, in->Ppad, dIdx, count, cum, sign,
+                                                                  in->logScalers ? 1 : 0, pBegin, pEnd);
     return cudaGetLastError();
 }
 

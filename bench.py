@@ -46,6 +46,11 @@ WORKLOADS = {
     "codon_mg94_500x5k": dict(taxa=500, patterns=5000, states=61, categories=1, rootHeight=0.1, treeSeed=2),
     # configs[0]-like latency case (benchmark1.xml shape: 1441 taxa, 593 patterns, HKY, no gamma)
     "hky_1441x593": dict(taxa=1441, patterns=593, states=4, categories=1, rootHeight=0.1, treeSeed=1441),
+    # configs[0] as shipped: the reference's own benchmark alignments (tests/golden/benchmark{1,2}_patterns.npz, extracted
+    # from examples/Benchmarks/benchmark{1,2}.xml), seeded coalescent start tree as the XMLs draw a random one
+    "benchmark1_xml": dict(taxa=1441, patterns=593, states=4, categories=1, rootHeight=0.05, treeSeed=666, fixture="benchmark1",
+                           scaling=True),      # underflows unscaled: evaluated the way BEAST does after its first underflow
+    "benchmark2_xml": dict(taxa=62, patterns=5565, states=4, categories=4, rootHeight=0.3, treeSeed=666, fixture="benchmark2"),
     # configs[3]-like: Makona-shaped synthetic (data absent from the reference tree)
     "makona_like_1610x6k": dict(taxa=1610, patterns=6000, states=4, categories=4, rootHeight=0.0025, treeSeed=3),
 }
@@ -62,8 +67,10 @@ def build_workload(name, shard_index, overrides):
         rng = np.random.default_rng(3)
         tree.branchRate = np.exp(rng.normal(0.0, 0.3, tree.nodeCount))     # relaxed clock folded into lengths
     if w["states"] == 4:
-        if name.startswith("hky"):
-            model = em.HKY(2.0, np.full(4, 0.25))
+        if name.startswith("hky") or name == "benchmark1_xml":
+            model = em.HKY(2.0, np.full(4, 0.25))                  # benchmark1.xml: <HKYModel> kappa 2, uniform frequencies
+        elif name == "benchmark2_xml":
+            model = em.GTR(1.0, 1.0, 1.0, 1.0, 1.0, 1.0, np.full(4, 0.25))   # benchmark2.xml:702-725 start values
         else:
             model = em.GTR(1.0, 4.0, 0.7, 1.2, 5.0, 1.0, np.array([0.30, 0.22, 0.24, 0.24]))
     elif w["states"] == 61:
@@ -77,7 +84,11 @@ def build_workload(name, shard_index, overrides):
     # the simulated alignment is cached per box (sweeps re-use it); it is regenerated when absent
     cache = os.path.join(os.environ.get("B200_BENCH_CACHE", "/tmp/b200_bench_cache"),
                          f"{name}_{w['taxa']}_{w['patterns']}_{w['states']}_{w['categories']}_{shard_index}.npz")
-    if os.path.exists(cache):
+    if w.get("fixture"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", w["fixture"] + "_patterns.npz"))
+        pats = em.Patterns(z["states"].astype(np.int32), z["weights"], 4)
+        assert pats.taxonCount == w["taxa"] and pats.patternCount == w["patterns"]
+    elif os.path.exists(cache):
         z = np.load(cache)
         pats = em.Patterns(z["states"], z["weights"], w["states"])
     else:
@@ -95,8 +106,9 @@ class Evaluation:
     """Pre-built call arguments of one full evaluation (what the Java side hands to JNI), in the two
     buffer-index parities BEAST's BufferIndexHelper alternates between."""
 
-    def __init__(self, tree, pats, model, site, traversal):
+    def __init__(self, tree, pats, model, site, traversal, scaling=False):
         self.tree, self.pats, self.model, self.site = tree, pats, model, site
+        self.scaling = scaling
         N, n = tree.tipCount, tree.nodeCount
         self.N, self.n = N, n
         like = tdl.TreeDataLikelihood.__new__(tdl.TreeDataLikelihood)
@@ -106,13 +118,16 @@ class Evaluation:
         self.lengths = np.array([t for _, t in like.branchOperations], dtype=np.float64)
         self.nodeOps = like.nodeOperations
         internal = n - N
-        self.ops, self.probIdx, self.rootIdx = [], [], []
+        self.ops, self.probIdx, self.rootIdx, self.scaleIdx, self.cumIdx = [], [], [], [], []
         for parity in (0, 1):
             pidx = lambda k: k if k < N else k + parity * internal       # BufferIndexHelper.getOffsetIndex
             midx = lambda k: k + parity * n
+            sidx = lambda k: (k - N) + parity * (internal + 1)           # scale buffers: BDLD:203,626-628,868-881
             ops = np.empty(len(self.nodeOps) * 7, dtype=np.int32)
             for q, (node, c1, c2) in enumerate(self.nodeOps):
-                ops[7 * q: 7 * q + 7] = (pidx(node), -1, -1, pidx(c1), midx(c1), pidx(c2), midx(c2))
+                ops[7 * q: 7 * q + 7] = (pidx(node), sidx(node) if scaling else -1, -1, pidx(c1), midx(c1), pidx(c2), midx(c2))
+            self.scaleIdx.append(np.array([sidx(node) for node, _, _ in self.nodeOps], dtype=np.int32))
+            self.cumIdx.append(internal + parity * (internal + 1))
             self.ops.append(ops)
             self.probIdx.append((self.branchNodes + parity * n).astype(np.int32))
             self.rootIdx.append(pidx(tree.root))
@@ -153,7 +168,12 @@ def issue_sync(inst, ev, parity, out):
     inst.setStateFrequencies(0, ev.model.getFrequencies())
     inst.updateTransitionMatrices(parity, ev.probIdx[parity], None, None, ev.lengths, len(ev.lengths))
     inst.updatePartials(ev.ops[parity], len(ev.nodeOps), -1)
-    inst.calculateRootLogLikelihoods(np.array([ev.rootIdx[parity]], dtype=np.int32), ZERO, ZERO, MINUS1, 1, out)
+    cum = MINUS1
+    if ev.scaling:             # BDLD:915-926
+        inst.resetScaleFactors(ev.cumIdx[parity])
+        inst.accumulateScaleFactors(ev.scaleIdx[parity], len(ev.nodeOps), ev.cumIdx[parity])
+        cum = np.array([ev.cumIdx[parity]], dtype=np.int32)
+    inst.calculateRootLogLikelihoods(np.array([ev.rootIdx[parity]], dtype=np.int32), ZERO, ZERO, cum, 1, out)
     return out[0]
 
 
@@ -252,7 +272,7 @@ def run_reference_arm(args, meta_base):
     build.build_oracle()
     w, tree, pats, model, site = build_workload(args.workload, 0, vars(args))
     S, C, P = w["states"], site.getCategoryCount(), pats.patternCount
-    ev = Evaluation(tree, pats, model, site, "POST_ORDER")
+    ev = Evaluation(tree, pats, model, site, "POST_ORDER", scaling=bool(w.get("scaling")))
     cores = os.cpu_count() or 1
     from oracle import cpu
     threads, tried = cpu_pick_threads(ev, S, C, P, cores)
@@ -328,7 +348,8 @@ def main():
 
     w, tree, pats, model, site = build_workload(args.workload, rank, vars(args))
     S, C, P = w["states"], site.getCategoryCount(), pats.patternCount
-    ev = Evaluation(tree, pats, model, site, "REVERSE_LEVEL_ORDER")     # what BEAST sends a non-CPU instance
+    scaling = bool(w.get("scaling"))
+    ev = Evaluation(tree, pats, model, site, "REVERSE_LEVEL_ORDER", scaling=scaling)     # what BEAST sends a non-CPU instance
     inst = create_instance(beagle.BeagleFactory.loadBeagleInstance, ev, S, C, P, [local_rank + 1, 0])
     lib = beagle.load_library()
 
@@ -336,7 +357,8 @@ def main():
     devp, strm = Cc.c_void_p(), Cc.c_void_p()
     out = np.zeros(1)
     logL = issue_sync(inst, ev, 0, out)
-    rc = lib.b200RootLogLikelihoodDevice(inst.instance, ev.rootIdx[0], 0, 0, -1, Cc.byref(devp), Cc.byref(strm))
+    rc = lib.b200RootLogLikelihoodDevice(inst.instance, ev.rootIdx[0], 0, 0, ev.cumIdx[0] if scaling else -1,
+                                         Cc.byref(devp), Cc.byref(strm))
     assert rc == 0
     stream = torch.cuda.ExternalStream(strm.value, device=torch.device("cuda", local_rank))
 
@@ -354,7 +376,12 @@ def main():
         # eigen system, rates and frequencies are resident (slot 0); buffers flip like BEAST's do
         inst.updateTransitionMatrices(0, ev.probIdx[p], None, None, ev.lengths, len(ev.lengths))
         inst.updatePartials(ev.ops[p], len(ev.nodeOps), -1)
-        lib.b200RootLogLikelihoodDevice(inst.instance, ev.rootIdx[p], 0, 0, -1, None, None)
+        cum = -1
+        if scaling:
+            inst.resetScaleFactors(ev.cumIdx[p])
+            inst.accumulateScaleFactors(ev.scaleIdx[p], len(ev.nodeOps), ev.cumIdx[p])
+            cum = ev.cumIdx[p]
+        lib.b200RootLogLikelihoodDevice(inst.instance, ev.rootIdx[p], 0, 0, cum, None, None)
         reduce_async()
 
     def step_e2e(k):
@@ -365,10 +392,16 @@ def main():
         inst.setStateFrequencies(0, ev.model.getFrequencies())
         inst.updateTransitionMatrices(p, ev.probIdx[p], None, None, ev.lengths, len(ev.lengths))
         inst.updatePartials(ev.ops[p], len(ev.nodeOps), -1)
+        cum = -1
+        if scaling:
+            inst.resetScaleFactors(ev.cumIdx[p])
+            inst.accumulateScaleFactors(ev.scaleIdx[p], len(ev.nodeOps), ev.cumIdx[p])
+            cum = ev.cumIdx[p]
         if world == 1:
-            inst.calculateRootLogLikelihoods(np.array([ev.rootIdx[p]], dtype=np.int32), ZERO, ZERO, MINUS1, 1, out)
+            inst.calculateRootLogLikelihoods(np.array([ev.rootIdx[p]], dtype=np.int32), ZERO, ZERO,
+                                             np.array([cum], dtype=np.int32), 1, out)
             return out[0]
-        lib.b200RootLogLikelihoodDevice(inst.instance, ev.rootIdx[p], 0, 0, -1, None, None)
+        lib.b200RootLogLikelihoodDevice(inst.instance, ev.rootIdx[p], 0, 0, cum, None, None)
         reduce_async()
         with torch.cuda.stream(stream):
             return float(dres.item())          # 8-byte D2H of the joint log-likelihood
@@ -423,7 +456,7 @@ def main():
 
     # ---- secondary: the incremental evaluation MCMC mostly issues (one tip-to-root path dirty) ------------
     inc = None
-    if world == 1:
+    if world == 1 and not scaling:
         issue_sync(inst, ev, 0, out)                       # parity-0 buffers hold the current state
         rng = np.random.default_rng(5)
         N, n, internal = ev.N, ev.n, ev.n - ev.N
@@ -506,7 +539,7 @@ def main():
         from beast_mcmc_b200 import build
         build.build_oracle()
         cores = os.cpu_count() or 1
-        evc = Evaluation(tree, pats, model, site, "POST_ORDER")
+        evc = Evaluation(tree, pats, model, site, "POST_ORDER", scaling=scaling)
         threads, tried = cpu_pick_threads(evc, S, C, P, cores)
         times, cval = cpu_time_evaluations(evc, S, C, P, threads, 3, args.cpu_budget)
         line["cpu_baseline"] = {"value": 1.0 / statistics.median(times), "unit": "evals/s", "cores": threads,

@@ -396,3 +396,58 @@ def test_full_size_properties():
     lo = tdl.TreeDataLikelihood(o, tree).getLogLikelihood()
     assert _rel(float(np.dot(sites[4000:4256], sl.weights)), lo) <= REL
     d.finalize()
+
+
+@pytest.mark.parametrize("name", ["benchmark1_xml", "benchmark2_xml"])
+def test_reference_benchmark_alignments(name):
+    """The reference's own benchmark inputs (examples/Benchmarks/benchmark{1,2}.xml, committed as pattern fixtures):
+    engine == C restatement of the reference algorithm, unscaled and rescaled, on the full alignment."""
+    import sys
+    sys.path.insert(0, H.ROOT)
+    import bench
+    from oracle import cpu
+    from beast_mcmc_b200 import build
+    build.build_oracle()
+    w, tree, pats, model, site = bench.build_workload(name, 0, {})
+    vals = []
+    for factory, res in ((GPU, [1, 0]), (cpu.factory(threads=4), None)):
+        for scheme in (S_.NONE, S_.ALWAYS):
+            d = tdl.BeagleDataLikelihoodDelegate(tree, pats, model, site, factory, resourceList=res, rescalingScheme=scheme,
+                                                 delayRescalingUntilUnderflow=False)
+            vals.append(tdl.TreeDataLikelihood(d, tree).getLogLikelihood())
+            d.finalize()
+    assert math.isfinite(vals[3])
+    assert _rel(vals[1], vals[3]) <= REL, vals          # engine rescaled == oracle rescaled
+    if math.isfinite(vals[2]):                          # benchmark1 (1441 taxa) underflows unscaled, as it does in BEAST
+        assert _rel(vals[3], vals[2]) <= REL and _rel(vals[0], vals[2]) <= REL, vals
+    else:
+        assert not math.isfinite(vals[0])
+
+
+def test_concurrent_instances_from_threads():
+    """CompoundLikelihood drives one instance per pool thread concurrently (CompoundLikelihood.java:63-82,198-241):
+    instances must not share mutable state.  Four instances evaluated from four Python threads (ctypes drops the
+    GIL inside the library) give exactly their serial values."""
+    import threading
+    cases = [H.synthetic_case(30 + 7 * k, 400 + 50 * k, 4, seed=40 + k) for k in range(4)]
+    serial = []
+    for tree, pats, model, site in cases:
+        d = _delegate(tree, pats, model, site, GPU, rescalingScheme=S_.ALWAYS, delayRescalingUntilUnderflow=False)
+        serial.append(tdl.TreeDataLikelihood(d, tree).getLogLikelihood())
+        d.finalize()
+    results = [[] for _ in cases]
+
+    def work(k):
+        tree, pats, model, site = cases[k]
+        d = _delegate(tree, pats, model, site, GPU, rescalingScheme=S_.ALWAYS, delayRescalingUntilUnderflow=False)
+        like = tdl.TreeDataLikelihood(d, tree)
+        for _ in range(15):
+            like.makeDirty()
+            results[k].append(like.getLogLikelihood())
+        d.finalize()
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for k in range(4):
+        assert len(results[k]) == 15 and all(v == serial[k] for v in results[k]), (k, serial[k], results[k][:3])
