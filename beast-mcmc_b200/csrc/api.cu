@@ -328,7 +328,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     int maxWindow = in->Ppad;
     {
         // patterns one warp owns: FMA kernel (32/CP)*R, tensor kernels 8*R resp. 16
-        const int patsPerWarp = !fourState ? 16 : (in->walkVariant == 2 ? 8 * std::min(in->walkR, 2) : (32 / in->matCP) * in->walkR);
+        const int patsPerWarp = !fourState ? 16 : (in->walkVariant == 2 ? 8 * in->tensorR : (32 / in->matCP) * in->walkR);
         const int warpsPerSM = fourState ? 32 : 12;      // resident warps the kernel family can hold per SM
         auto wantSubsFor = [&](int window) {
             const int warpsPerSub = std::max(1, (window + patsPerWarp - 1) / patsPerWarp);
@@ -568,7 +568,8 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
         int cp = 1;
         while (cp < in->C) cp <<= 1;
         in->matCP = cp;
-        in->matStride = (size_t)16 * cp + 32 * (size_t)in->C;     // [j][CP][i] + M[c][i][j] + MT[c][j][i]
+        in->matStride = (size_t)16 * cp + 52 * (size_t)in->C;     // [j][CP][i] + Mpad[c][8][4] + MTg[c][5][4]
+        in->matStride = (in->matStride + 3) & ~size_t(3);        // keep every buffer 32-byte aligned
     } else {
         in->matCP = 0;
         in->matStride = 2 * (size_t)in->C * in->Sp * in->Sp;     // MT[c][j][i] then M[c][i][j] (tensor-path B operand)
@@ -585,6 +586,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->phaseSmall = envInt("B200_PHASE_SMALL", 24);
     in->phaseOversub = std::max(1, envInt("B200_PHASE_OVERSUB", 2));
     in->walkMinBlocks = envInt("B200_WALK_MINB", 4);
+    in->tensorR = envInt("B200_TENSOR_R", 2) >= 4 ? 4 : 2;
     in->genericMma = envInt("B200_GENERIC_MMA", 1);
     in->mmaWarps = envInt("B200_MMA_WARPS", 4) == 8 ? 8 : 4;     // 8 = 256-thread blocks with cp.async double buffering
     in->walkR = envInt("B200_WALK_R", 4);
@@ -918,8 +920,14 @@ int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMat
                 const double v = inMatrix[((size_t)c * in->S + i) * in->S + j];
                 t[matIndex(in, c, i, j)] = v;
                 if (in->matCP) {
-                    t[16 * in->matCP + (size_t)c * 16 + i * 4 + j] = v;
-                    t[16 * in->matCP + (size_t)in->C * 16 + (size_t)c * 16 + j * 4 + i] = v;
+                    double* mm = t.data() + 16 * in->matCP;
+                    mm[(size_t)c * 32 + i * 4 + j] = v;
+                    double* mt = mm + (size_t)in->C * 32;
+                    mt[(size_t)c * 20 + j * 4 + i] = v;
+                    for (int q = 0; q < 4; ++q) {
+                        if (in->S < 4) mt[(size_t)c * 20 + in->S * 4 + q] = q < in->S ? 1.0 : 0.0;
+                        else mt[(size_t)c * 20 + 16 + q] = 1.0;
+                    }
                 } else {
                     t[(size_t)in->C * in->Sp * in->Sp + ((size_t)c * in->Sp + i) * in->Sp + j] = v;
                 }

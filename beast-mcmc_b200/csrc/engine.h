@@ -108,6 +108,7 @@ struct Instance {
     int stackDepthMax = 12;
     int walkMinBlocks = 4;       // __launch_bounds__(128, n) variant of the 4-state walk (4, 5 or 6)
     int mmaWarps = 4;            // codon-size tensor walk: 4 warps single-buffered (default) or 8 warps double-buffered
+    int tensorR = 2;             // 8-pattern tiles per warp in the 4-state tensor walk (2 or 4)
     int genericMma = 1;          // S > 4: 1 = fp64 tensor-core block walk, 0 = FMA block walk
     int walkR = 4;               // patterns per thread in the 4-state walk (1, 2 or 4)
     int phaseTmin = 4, phaseOversub = 2, phaseSmall = 24;   // phaseSmall: a remainder this short runs as one launch

@@ -101,10 +101,15 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
             // generic layout: second half of the buffer holds the row-major M[c][i][j] (tensor-path B operand)
             matBase[(size_t)probIdx[b] * matStride + (size_t)C * Sp * Sp + ((size_t)c * Sp + i) * Sp + j] = acc;
         } else {
-            // tensor-core path copies after the [j][CP][i] block: M[c][i][j] (B fragments) and MT[c][j][i] (tip columns)
+            // tensor-path copies after the [j][CP][i] block (k_walk4t):
+            //   Mpad[c][8][4] : B fragment, lane (g,t) reads [g][t]; rows g >= 4 stay zero
+            //   MTg [c][5][4] : column s of P for a compact tip in state s, plus the gap column s == S = (1,..,1,0..)
             double* mm = matBase + (size_t)probIdx[b] * matStride + 16 * matCP;
-            mm[(size_t)c * 16 + i * 4 + j] = acc;
-            mm[(size_t)C * 16 + (size_t)c * 16 + j * 4 + i] = acc;
+            mm[(size_t)c * 32 + i * 4 + j] = acc;
+            mm[(size_t)c * 32 + 16 + i * 4 + j] = 0.0;
+            double* mt = mm + (size_t)C * 32;
+            mt[(size_t)c * 20 + j * 4 + i] = (j < S) ? acc : ((j == S && i < S) ? 1.0 : 0.0);
+            if (j == 0) mt[(size_t)c * 20 + 16 + i] = (S == 4 && i < S) ? 1.0 : 0.0;
         }
     }
 }
@@ -422,86 +427,73 @@ static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int4* dSubs
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4-state walk on the FP64 tensor pipe (DMMA m8n8k4)
+// 4-state walk on the FP64 tensor pipe (DMMA m8n8k4)  --  B200_WALK_VARIANT=2
 // ---------------------------------------------------------------------------------------------
 // D[p][i] = sum_j X[p][j] * P[i][j]  as one mma.sync.m8n8k4.f64 per (8 patterns, category, child):
 //   A fragment = child partials  [8 patterns][4 states]   lane (g,t) <- X[p0+g][t]     (256 contiguous bytes / warp)
-//   B fragment = transition rows [4 (j)][8 (i)]            lane (g,t) <- P[g][t], 0 for g >= 4 (128 contiguous bytes)
-//   D fragment                    [8 patterns][8 (i)]      lane (g,t) -> i = 2t,2t+1 of pattern g (valid for t < 2)
+//   B fragment = transition rows [4 (j)][8 (i)]            lane (g,t) <- Mpad[g][t]     (256 contiguous bytes, rows >= 4 zero)
+//   D fragment                    [8 patterns][8 (i)]      lane (g,t) -> i = 2t,2t+1 of pattern g (meaningful for t < 2)
 // tcgen05 has no fp64 kind, so the fp64 tensor path on sm_100a is mma.sync (SASS DMMA.8x8x4).
-// Compared with the FMA kernel the matrix reaches the register file ONCE per warp (8 B/lane) instead of
-// once per thread (128 B/lane), which was what saturated the LSU->RF path.
-// Warp = all C categories x R tiles of 8 patterns; results stay in registers until the per-pattern
-// maximum over categories is known, so the rescale is fused.
+// The matrix reaches the register file ONCE per warp (8 B/lane) instead of once per thread (128 B/lane),
+// which is what saturates the LSU->RF path of the FMA kernel.  Everything is arranged so that loads need
+// no predicates: pattern rows are padded to 32, gap tips read a ones-column, B rows 4..7 are stored zeros;
+// only stores (and scale-factor writes) are masked.  Warp = C categories x R tiles of 8 patterns.
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
         : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
 }
 
-template <int CMAX, int R>
-__global__ void __launch_bounds__(128)
-k_walk4m(const WalkArgs A) {
+template <int C, int R, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_walk4t(const WalkArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int g = lane >> 2, t = lane & 3;
     const int4 range = __ldg(A.subs + blockIdx.y);
-    const int pLimit = range.w;
-    if (range.z + warp * (8 * R) >= pLimit) return;
-    const int pBase = range.z + warp * (8 * R) + g;        // pattern of tile r: pBase + 8 r
-    const int S = A.S, C = A.C;
+    if (range.z + warp * (8 * R) >= range.w) return;
+    const int g = lane >> 2, t = lane & 3;
+    const int pBase = range.z + warp * (8 * R) + g;        // pattern of tile r: pBase + 8 r   (always < Ppad)
     const size_t mstride = A.matStride;
-    const int last = range.y - 1;
     const size_t catStride = (size_t)A.Ppad * 4;
+    const size_t cellOff = (size_t)pBase * 4;
+    const int last = range.y - 1;
+    const double* matB = A.mats + A.matMmaOffset + lane;                    // Mpad[c][g][t] = + c*32
+    const double* matT = A.mats + A.matMmaOffset + C * 32 + 2 * (t & 1);     // MTg[c][s][2t..] = + c*20 + s*4
 
     Op4 cur = loadOp(A.ops + range.x);
     for (int k = range.x; k <= last; ++k) {
         const Op4 nxt = loadOp(A.ops + min(k + 1, last));
-        double y[CMAX][R][2];
-        bool act[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int p = pBase + 8 * r;
-            act[r] = p < pLimit && p >= cur.pBegin && p < cur.pEnd;
-        }
+        double y[C][R][2];
 #pragma unroll
         for (int child = 0; child < 2; ++child) {
             const int cb = child == 0 ? cur.c1 : cur.c2;
-            const double* mm = A.mats + (size_t)(child == 0 ? cur.m1 : cur.m2) * mstride + A.matMmaOffset;
+            const size_t moff = (size_t)(child == 0 ? cur.m1 : cur.m2) * mstride;
             if (cb >= 0) {
-                const double* x = A.partials + (size_t)cb * A.stride + (size_t)pBase * 4 + t;
+                const double* x = A.partials + (size_t)cb * A.stride + cellOff + t;
+                double b[C];
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c) {
-                    if (c < C) {
-                        const double b = (g < 4) ? __ldg(mm + c * 16 + g * 4 + t) : 0.0;
+                for (int c = 0; c < C; ++c) b[c] = __ldg(matB + moff + c * 32);
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            double a = 0.0, d0, d1;
-                            if (act[r]) asm volatile("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(x + c * catStride + (size_t)r * 32) : "memory");
-                            dmma884(d0, d1, a, b);
-                            if (child == 0) { y[c][r][0] = d0; y[c][r][1] = d1; }
-                            else { y[c][r][0] *= d0; y[c][r][1] *= d1; }
-                        }
+                for (int c = 0; c < C; ++c) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        double a, d0, d1;
+                        asm volatile("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(x + c * catStride + r * 32) : "memory");
+                        dmma884(d0, d1, a, b[c]);
+                        if (child == 0) { y[c][r][0] = d0; y[c][r][1] = d1; }
+                        else { y[c][r][0] *= d0; y[c][r][1] *= d1; }
                     }
                 }
             } else {
-                const uint8_t* st = A.states + (size_t)(-cb - 1) * A.Ppad;
-                const double* mt = mm + (size_t)C * 16;              // MT[c][j][i]
+                const uint8_t* st = A.states + (size_t)(-cb - 1) * A.Ppad + pBase;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const int p = pBase + 8 * r;
-                    const int s = act[r] ? (int)__ldg(st + p) : S;
+                    const int s = (int)__ldg(st + 8 * r);                    // gap/unknown is stored as S -> ones column
+                    const double* col = matT + moff + s * 4;
 #pragma unroll
-                    for (int c = 0; c < CMAX; ++c) {
-                        if (c < C) {
-                            double v0 = (2 * t < S) ? 1.0 : 0.0, v1 = (2 * t + 1 < S) ? 1.0 : 0.0;
-                            if (s < S && t < 2) {
-                                const double2 col = __ldg(reinterpret_cast<const double2*>(mt + c * 16 + s * 4 + 2 * t));
-                                v0 = col.x; v1 = col.y;
-                            }
-                            if (t >= 2) { v0 = 0.0; v1 = 0.0; }
-                            if (child == 0) { y[c][r][0] = v0; y[c][r][1] = v1; }
-                            else { y[c][r][0] *= v0; y[c][r][1] *= v1; }
-                        }
+                    for (int c = 0; c < C; ++c) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(col + c * 20));
+                        if (child == 0) { y[c][r][0] = v.x; y[c][r][1] = v.y; }
+                        else { y[c][r][0] *= v.x; y[c][r][1] *= v.y; }
                     }
                 }
             }
@@ -511,53 +503,52 @@ k_walk4m(const WalkArgs A) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int p = pBase + 8 * r;
+                const bool act = p >= cur.pBegin && p < cur.pEnd;
                 double f;
                 if (cur.sw >= 0) {
                     double m = 0.0;
 #pragma unroll
-                    for (int c = 0; c < CMAX; ++c) if (c < C) m = fmax(m, fmax(y[c][r][0], y[c][r][1]));
-                    if (!act[r] || t >= 2) m = 0.0;
+                    for (int c = 0; c < C; ++c) m = fmax(m, fmax(y[c][r][0], y[c][r][1]));
+                    if (t >= 2) m = 0.0;                                     // lanes t >= 2 carry no states
                     m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
                     m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
                     if (m == 0.0) m = 1.0;
                     f = m;
-                    if (act[r] && t == 0) {
+                    if (act && t == 0) {
                         const double lm = log(m);
                         A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
                         if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
                     }
                 } else {
-                    f = act[r] ? A.scale[(size_t)cur.sr * A.Ppad + p] : 1.0;
+                    f = act ? A.scale[(size_t)cur.sr * A.Ppad + p] : 1.0;
                     if (A.logScalers) f = exp(f);
                 }
                 const double inv = 1.0 / f;
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c) if (c < C) { y[c][r][0] *= inv; y[c][r][1] *= inv; }
+                for (int c = 0; c < C; ++c) { y[c][r][0] *= inv; y[c][r][1] *= inv; }
             }
-            __syncwarp();
         }
         // ---- store: lanes t < 2 own states 2t, 2t+1 (16 B) of pattern g ---------------------------
         {
-            double* dst = A.partials + (size_t)cur.dest * A.stride + (size_t)pBase * 4 + 2 * t;
+            double* dst = A.partials + (size_t)cur.dest * A.stride + cellOff + 2 * t;
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c) {
-                if (c < C) {
+            for (int r = 0; r < R; ++r) {
+                const int p = pBase + 8 * r;
+                if (t < 2 && p >= cur.pBegin && p < cur.pEnd) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        if (act[r] && t < 2)
-                            asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(dst + c * catStride + (size_t)r * 32),
-                                         "d"(y[c][r][0]), "d"(y[c][r][1]) : "memory");
-                    }
+                    for (int c = 0; c < C; ++c)
+                        asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(dst + c * catStride + r * 32),
+                                     "d"(y[c][r][0]), "d"(y[c][r][1]) : "memory");
                 }
             }
         }
-        __syncwarp();          // the next op may read (other lanes of this warp) what was just stored
+        __syncwarp();          // the next op may read (through other lanes of this warp) what was just stored
         cur = nxt;
     }
 }
 
-template <int CMAX, int R>
-static cudaError_t launchWalk4M(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int maxWindow) {
+template <int C, int R>
+static cudaError_t launchWalk4Tensor(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     const int warps = (maxWindow + 8 * R - 1) / (8 * R);
     dim3 grid((warps + 3) / 4, nSubs);
     WalkArgs A;
@@ -565,19 +556,21 @@ static cudaError_t launchWalk4M(Instance* in, const Op4* dOps, const int4* dSubs
     A.states = in->states8Base; A.mats = in->dMat; A.scale = in->dScale;
     A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.logScalers = in->logScalers ? 1 : 0;
     A.matStride = in->matStride; A.matMmaOffset = 16 * in->matCP;
-    k_walk4m<CMAX, R><<<grid, 128, 0, in->stream>>>(A);
+    if (in->walkMinBlocks >= 6) k_walk4t<C, R, 6><<<grid, 128, 0, in->stream>>>(A);
+    else k_walk4t<C, R, 4><<<grid, 128, 0, in->stream>>>(A);
     return cudaGetLastError();
 }
 
+// exact category counts only (fully unrolled); anything else stays on the FMA kernel
+static bool walk4TensorSupported(const Instance* in) { return in->C == 1 || in->C == 2 || in->C == 4 || in->C == 8; }
+
 static cudaError_t launchWalk4Mma(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int maxWindow) {
-    const bool r2 = in->walkR >= 2;
-    switch (in->matCP) {
-        case 1: return r2 ? launchWalk4M<1, 2>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4M<1, 1>(in, dOps, dSubs, nSubs, maxWindow);
-        case 2: return r2 ? launchWalk4M<2, 2>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4M<2, 1>(in, dOps, dSubs, nSubs, maxWindow);
-        case 4: return r2 ? launchWalk4M<4, 2>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4M<4, 1>(in, dOps, dSubs, nSubs, maxWindow);
-        case 8: return r2 ? launchWalk4M<8, 2>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4M<8, 1>(in, dOps, dSubs, nSubs, maxWindow);
-        case 16: return launchWalk4M<16, 1>(in, dOps, dSubs, nSubs, maxWindow);
-        default: return launchWalk4M<32, 1>(in, dOps, dSubs, nSubs, maxWindow);
+    const bool r4 = in->tensorR >= 4;
+    switch (in->C) {
+        case 1: return r4 ? launchWalk4Tensor<1, 4>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4Tensor<1, 2>(in, dOps, dSubs, nSubs, maxWindow);
+        case 2: return r4 ? launchWalk4Tensor<2, 4>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4Tensor<2, 2>(in, dOps, dSubs, nSubs, maxWindow);
+        case 4: return r4 ? launchWalk4Tensor<4, 4>(in, dOps, dSubs, nSubs, maxWindow) : launchWalk4Tensor<4, 2>(in, dOps, dSubs, nSubs, maxWindow);
+        default: return launchWalk4Tensor<8, 2>(in, dOps, dSubs, nSubs, maxWindow);
     }
 }
 
@@ -592,7 +585,7 @@ static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int4* dSubs
 
 cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder) {
     if (nSubs <= 0) return cudaSuccess;
-    if (in->walkVariant == 2 && !preOrder) return launchWalk4Mma(in, dOps, dSubs, nSubs, maxWindow);
+    if (in->walkVariant == 2 && !preOrder && walk4TensorSupported(in)) return launchWalk4Mma(in, dOps, dSubs, nSubs, maxWindow);
     switch (in->matCP) {
         case 1: return launchWalk4T<1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
         case 2: return launchWalk4T<2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);

@@ -154,20 +154,23 @@ def test_mcmc_reenactment_store_restore():
 
 
 def test_walk_variants_agree():
-    """operand-stack walk == direct-global walk == caller order (bitwise: same arithmetic)."""
+    """FMA walk: operand-stack == direct-global == caller order, bitwise (same arithmetic).  The tensor-core
+    variant (DMMA accumulates the 4-term dot product in its own order) agrees to rounding."""
     import os
     tree, pats, model, site = H.synthetic_case(120, 700, 4, seed=4)
-    vals = []
-    for variant, reorder, depth in [("0", "0", "12"), ("0", "1", "12"), ("1", "1", "12"), ("1", "1", "2"), ("1", "0", "3")]:
+    vals, tensor = [], []
+    for variant, reorder, depth in [("0", "0", "12"), ("0", "1", "12"), ("1", "1", "12"), ("1", "1", "2"), ("1", "0", "3"),
+                                    ("2", "1", "12"), ("2", "0", "12")]:
         os.environ["B200_WALK_VARIANT"], os.environ["B200_REORDER"], os.environ["B200_STACK_DEPTH"] = variant, reorder, depth
         try:
             d = _delegate(tree, pats, model, site, GPU, rescalingScheme=S_.ALWAYS, delayRescalingUntilUnderflow=False)
-            vals.append(tdl.TreeDataLikelihood(d, tree).getLogLikelihood())
+            (tensor if variant == "2" else vals).append(tdl.TreeDataLikelihood(d, tree).getLogLikelihood())
             d.finalize()
         finally:
             for k in ("B200_WALK_VARIANT", "B200_REORDER", "B200_STACK_DEPTH"):
                 os.environ.pop(k, None)
     assert all(v == vals[0] for v in vals), vals
+    assert all(_rel(v, vals[0]) <= 1e-13 for v in tensor), (tensor, vals[0])
 
 
 def test_by_partition_equals_separate_instances():
