@@ -1252,6 +1252,29 @@ int beagleCalculateEdgeDerivatives(int instance, const int* postBufferIndices, c
     return BEAGLE_SUCCESS;
 }
 
+// ---- host-logic test hook (no CUDA calls): the execution plan of an operation list -----------------
+int b200DebugPlan(const int* operations, int operationCount, int bufferCount, int fixedT, int wantSubs, int minT,
+                  int smallRemainder, int preOrder, int* outOrder, int* outSubs, int* outPhaseStart, int* outCounts) {
+    if (operationCount < 0 || bufferCount <= 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<HostOp> hops(operationCount);
+    for (int k = 0; k < operationCount; ++k) {
+        const int* o = operations + 7 * k;
+        for (int f : {o[0], o[3], o[5]}) if (f < 0 || f >= bufferCount) return BEAGLE_ERROR_OUT_OF_RANGE;
+        hops[k] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], 0, -1};
+        hops[k].kind = preOrder ? 1 : 0;
+    }
+    Plan plan;
+    if (operationCount == 0) { outCounts[0] = outCounts[1] = 0; return BEAGLE_SUCCESS; }
+    if (preOrder) planLevels(hops, bufferCount, plan);
+    else planPhases(hops, bufferCount, true, fixedT, std::max(1, wantSubs), std::max(1, minT), smallRemainder, plan);
+    for (int k = 0; k < operationCount; ++k) outOrder[k] = plan.order[k];
+    for (size_t q = 0; q < plan.subs.size(); ++q) { outSubs[2 * q] = plan.subs[q].begin; outSubs[2 * q + 1] = plan.subs[q].end; }
+    for (size_t q = 0; q < plan.phaseStart.size(); ++q) outPhaseStart[q] = plan.phaseStart[q];
+    outCounts[0] = (int)plan.subs.size();
+    outCounts[1] = (int)plan.phaseStart.size() - 1;
+    return BEAGLE_SUCCESS;
+}
+
 // ---- engine extensions ------------------------------------------------------------------------
 int b200SetKernelTiming(int instance, int enable) {
     GET_INSTANCE(in, instance);

@@ -310,6 +310,14 @@ BEAGLE_DLLEXPORT int b200RootLogLikelihoodDevice(int instance, int bufferIndex, 
                                                  int stateFrequenciesIndex, int cumulativeScaleIndex,
                                                  void** outDevicePointer, void** outStream);
 
+/* Host-logic test hook (no CUDA): the engine's execution plan for a 7-int-per-op list.  outOrder[n] = execution
+ * position -> caller index; outSubs = (begin,end) position pairs of the independent subtree walks, grouped by phase;
+ * outPhaseStart = index of each phase's first subtree (phases+1 entries); outCounts = {subtrees, phases}.
+ * Array capacities: outSubs 2n ints, outPhaseStart n+1 ints. */
+BEAGLE_DLLEXPORT int b200DebugPlan(const int* operations, int operationCount, int bufferCount, int fixedT, int wantSubs,
+                                   int minT, int smallRemainder, int preOrder, int* outOrder, int* outSubs,
+                                   int* outPhaseStart, int* outCounts);
+
 #ifdef __cplusplus
 }
 #endif
