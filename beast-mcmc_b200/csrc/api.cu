@@ -383,7 +383,27 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     // position of its LAST reader inside this list (before the buffer is re-written); the forward
     // pass then parks results in slots and frees each slot at that last read.
     const bool preOrder = hops[0].kind == 1;
-    const int maxDepth = (fourState && in->walkVariant == 1 && !preOrder) ? in->stackDepthMax : 0;
+    // The operand stack pays off where a phase is LATENCY-bound (few walks in flight: the tail of a full
+    // evaluation, or the short dependent chain of an incremental update): it removes the store -> L2 -> load round
+    // trip from every op of the chain.  Throughput-bound phases run without it (shared memory would cap occupancy).
+    const bool stackEverywhere = fourState && in->walkVariant == 1 && !preOrder;
+    const bool stackThin = fourState && in->walkVariant == 0 && in->stackTail && !preOrder;
+    const int maxDepth = (stackEverywhere || stackThin) ? in->stackDepthMax : 0;
+    const int nPhases = (int)plan.phaseStart.size() - 1;
+    std::vector<char> subStack(plan.subs.size(), 0);
+    std::vector<int> phaseDepth(std::max(nPhases, 1), 0), phaseOfSub(plan.subs.size(), 0);
+    if (maxDepth > 0) {
+        const int patsPerWarpS = (32 / in->matCP) * in->walkR;
+        for (int ph = 0; ph < nPhases; ++ph) {
+            long warps = 0;
+            for (int q = plan.phaseStart[ph]; q < plan.phaseStart[ph + 1]; ++q) {
+                warps += (plan.subs[q].pLimit - plan.subs[q].pBase + patsPerWarpS - 1) / patsPerWarpS;
+                phaseOfSub[q] = ph;
+            }
+            const bool thin = warps < (long)in->smCount * 8;
+            for (int q = plan.phaseStart[ph]; q < plan.phaseStart[ph + 1]; ++q) subStack[q] = stackEverywhere || thin;
+        }
+    }
     std::vector<int> lastReadOfProd(maxDepth > 0 ? n : 0, -1);
     std::vector<int> subOfPos(n, 0);
     for (int sIdx = 0; sIdx < (int)plan.subs.size(); ++sIdx)
@@ -391,7 +411,9 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     if (maxDepth > 0) {
         // per subtree: the stack is private to a (subtree, tile) walk
         std::vector<int> lastRead(in->nBuffers, -1);
-        for (const Sub& sb : plan.subs) {
+        for (size_t sIdx = 0; sIdx < plan.subs.size(); ++sIdx) {
+            if (!subStack[sIdx]) continue;
+            const Sub& sb = plan.subs[sIdx];
             for (int pos = sb.end - 1; pos >= sb.begin; --pos) {
                 const HostOp& o = hops[order[pos]];
                 lastReadOfProd[pos] = lastRead[o.dest];
@@ -422,7 +444,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             freeSlots.clear();
             depthThisSub = 0;
         }
-        if (maxDepth > 0) {
+        if (maxDepth > 0 && subStack[subOfPos[pos]]) {
             auto take = [&](int buf, bool isTip) -> int {
                 if (isTip) return -1;
                 const int slot = slotOf[buf];
@@ -435,7 +457,11 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             if (lastReadOfProd[pos] > pos) {         // a later op of this list reads the result
                 int slot = -1;
                 if (!freeSlots.empty()) { slot = freeSlots.back(); freeSlots.pop_back(); }
-                else if (depthThisSub < maxDepth) { slot = depthThisSub++; depthUsed = std::max(depthUsed, depthThisSub); }
+                else if (depthThisSub < maxDepth) {
+                    slot = depthThisSub++;
+                    depthUsed = std::max(depthUsed, depthThisSub);
+                    phaseDepth[phaseOfSub[subOfPos[pos]]] = std::max(phaseDepth[phaseOfSub[subOfPos[pos]]], depthThisSub);
+                }
                 if (slot >= 0) { slotOf[o.dest] = slot; slotFreeAt[o.dest] = lastReadOfProd[pos]; dstSlot = slot; }
             }
         }
@@ -489,7 +515,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         const int s0 = plan.phaseStart[ph], s1 = plan.phaseStart[ph + 1];
         if (s1 <= s0) continue;
         TimedScope ts(in, T_PARTIALS);
-        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, depthUsed, maxWindow, preOrder)
+        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0,
+                                   maxDepth > 0 ? phaseDepth[ph] : 0, maxWindow, preOrder)
                      : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, maxWindow, preOrder);
     }
     if (tmp != nullptr) { cudaStreamSynchronize(in->stream); cudaFree(tmp); }
@@ -581,6 +608,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 0);
     in->reorder = envInt("B200_REORDER", 1);
+    in->stackTail = envInt("B200_STACK_TAIL", 0);     // measured slower (0.458 vs 0.436 ms): off by default
     in->phaseT = envInt("B200_PHASE_T", 0);
     in->phaseTmin = std::max(1, envInt("B200_PHASE_TMIN", 4));
     in->phaseSmall = envInt("B200_PHASE_SMALL", 24);
