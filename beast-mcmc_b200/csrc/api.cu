@@ -608,6 +608,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 0);
     in->reorder = envInt("B200_REORDER", 1);
+    in->thinR1 = envInt("B200_THIN_R1", 1);
     in->stackTail = envInt("B200_STACK_TAIL", 0);     // measured slower (0.458 vs 0.436 ms): off by default
     in->phaseT = envInt("B200_PHASE_T", 0);
     in->phaseTmin = std::max(1, envInt("B200_PHASE_TMIN", 4));

@@ -105,6 +105,7 @@ struct Instance {
     int walkBlock = 128;
     int walkVariant = 0;
     int reorder = 1;
+    int thinR1 = 1;              // thin (latency-bound) phases of the 4-state walk use one pattern group per thread
     int stackTail = 0;           // operand stack for latency-bound (thin) phases of the 4-state walk (experiment, off)
     int stackDepthMax = 12;
     int walkMinBlocks = 4;       // __launch_bounds__(128, n) variant of the 4-state walk (4, 5 or 6)

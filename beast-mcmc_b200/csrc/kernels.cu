@@ -576,6 +576,10 @@ static cudaError_t launchWalk4Mma(Instance* in, const Op4* dOps, const int4* dSu
 
 template <int CP>
 static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder) {
+    // a thin phase (few walks in flight) is latency-bound: one pattern group per thread gives 4x the warps per op
+    const long walks = (long)nSubs * ((maxWindow + (32 / CP) * in->walkR - 1) / ((32 / CP) * in->walkR));
+    if (in->thinR1 && !preOrder && stackDepth == 0 && walks < (long)in->smCount * 8)
+        return launchWalk4R<CP, 1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
     switch (in->walkR) {
         case 4: return launchWalk4R<CP, 4>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
         case 2: return launchWalk4R<CP, 2>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
