@@ -127,6 +127,7 @@ void destroyInstance(Instance* in) {
     cudaSetDevice(in->device);
     if (in->stream) cudaStreamSynchronize(in->stream);
     cudaFree(in->partialsBase); cudaFree(in->states8Base); cudaFree(in->states32Base);
+    for (CachedPlan& cp : in->planCache) cudaFree(cp.dBlock);
     cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dRates); cudaFree(in->dWeights);
     cudaFree(in->dFreqs); cudaFree(in->dScale); cudaFree(in->dPatternWeights);
     cudaFree(in->dPatternPartitions); cudaFree(in->dSite); cudaFree(in->dBlockSums); cudaFree(in->dOut);
@@ -178,7 +179,6 @@ char gImplName[] = "B200-CUDA-Double";
 char gImplDesc[] = "sm_100a walk kernels: one launch per operation list, shared-memory operand stack";
 
 // ---- op planning ------------------------------------------------------------------------------
-struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; int kind = 0; };   // kind 1 = pre-order op
 
 // Execution plan of one operation list.
 //
@@ -301,9 +301,39 @@ void planLevels(const std::vector<HostOp>& ops, int nBuffers, Plan& plan) {
     plan.phaseStart.push_back((int)plan.subs.size());
 }
 
+// launch the phases of a prepared plan (device-resident op records + subtree table)
+cudaError_t launchPlan(Instance* in, const void* dOps, const void* dSubs, const std::vector<int>& phaseStart,
+                       const std::vector<int>& phaseDepth, bool fourPath, int maxWindow, bool preOrder) {
+    cudaError_t e = cudaSuccess;
+    for (size_t ph = 0; ph + 1 < phaseStart.size() && e == cudaSuccess; ++ph) {
+        const int s0 = phaseStart[ph], s1 = phaseStart[ph + 1];
+        if (s1 <= s0) continue;
+        TimedScope ts(in, T_PARTIALS);
+        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0,
+                                   ph < phaseDepth.size() ? phaseDepth[ph] : 0, maxWindow, preOrder)
+                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0,
+                                         maxWindow, preOrder);
+    }
+    return e;
+}
+
 int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartition) {
     const int n = (int)hops.size();
     if (n == 0) return BEAGLE_SUCCESS;
+    // ---- plan cache: MCMC re-issues identical lists all the time (every move that keeps the topology and
+    // dirties all nodes, in BEAST's two buffer-index parities); a hit skips validation, planning and the H2D copy.
+    static_assert(sizeof(HostOp) == 10 * sizeof(int), "HostOp is compared bytewise");
+    if (in->planCacheSize > 0) {
+        for (CachedPlan& cp : in->planCache) {
+            if (cp.dBlock == nullptr || cp.n != n || cp.byPartition != byPartition || cp.epoch != in->bufferEpoch ||
+                memcmp(cp.key.data(), hops.data(), sizeof(HostOp) * (size_t)n) != 0)
+                continue;
+            cp.lastUse = ++in->planClock;
+            CUDA_OK(launchPlan(in, cp.dBlock, static_cast<char*>(cp.dBlock) + cp.subsOffset, cp.phaseStart, cp.phaseDepth,
+                               cp.fourPath, cp.maxWindow, cp.preOrder));
+            return BEAGLE_SUCCESS;
+        }
+    }
     // ---- validation + lazy allocation
     for (const HostOp& o : hops) {
         if (!validRange(o.dest, in->nBuffers) || !validRange(o.c1, in->nBuffers) ||
@@ -315,6 +345,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         if (o.cum != BEAGLE_OP_NONE && !validRange(o.cum, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
         if (byPartition && !validRange(o.part, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
         if (ensurePartials(in, o.dest) == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+        if (in->states32[o.dest] != nullptr) in->bufferEpoch++;
         in->states8[o.dest] = nullptr;      // a written buffer holds partials from now on
         in->states32[o.dest] = nullptr;
     }
@@ -510,14 +541,31 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         CUDA_OK(cudaMemcpyAsync(dSubs, plan.subs.data(), subBytes, cudaMemcpyHostToDevice, in->stream));
         CUDA_OK(cudaStreamSynchronize(in->stream));
     }
-    cudaError_t e = cudaSuccess;
-    for (size_t ph = 0; ph + 1 < plan.phaseStart.size() && e == cudaSuccess; ++ph) {
-        const int s0 = plan.phaseStart[ph], s1 = plan.phaseStart[ph + 1];
-        if (s1 <= s0) continue;
-        TimedScope ts(in, T_PARTIALS);
-        e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0,
-                                   maxDepth > 0 ? phaseDepth[ph] : 0, maxWindow, preOrder)
-                     : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, maxWindow, preOrder);
+    std::vector<int> depths(plan.phaseStart.size(), 0);
+    for (size_t ph = 0; ph + 1 < plan.phaseStart.size(); ++ph) depths[ph] = (maxDepth > 0 && ph < phaseDepth.size()) ? phaseDepth[ph] : 0;
+    cudaError_t e = launchPlan(in, dOps, dSubs, plan.phaseStart, depths, fourPath, maxWindow, preOrder);
+    if (e == cudaSuccess && tmp == nullptr && in->planCacheSize > 0) {
+        // remember the plan: device copy of the records (stream-ordered D2D out of the staging ring)
+        if ((int)in->planCache.size() < in->planCacheSize) in->planCache.emplace_back();
+        CachedPlan* slot = &in->planCache[0];
+        for (CachedPlan& cp : in->planCache) if (cp.dBlock == nullptr || cp.lastUse < slot->lastUse) slot = &cp;
+        const size_t subsOffset = (opBytes + 255) & ~size_t(255);
+        const size_t need = subsOffset + subBytes;
+        if (slot->capacity < need) {
+            if (slot->dBlock) cudaFree(slot->dBlock);
+            slot->dBlock = nullptr; slot->capacity = 0;
+            if (cudaMalloc(&slot->dBlock, need) == cudaSuccess) slot->capacity = need; else cudaGetLastError();
+        }
+        if (slot->dBlock != nullptr &&
+            cudaMemcpyAsync(slot->dBlock, dOps, opBytes, cudaMemcpyDeviceToDevice, in->stream) == cudaSuccess &&
+            cudaMemcpyAsync(static_cast<char*>(slot->dBlock) + subsOffset, dSubs, subBytes, cudaMemcpyDeviceToDevice, in->stream) == cudaSuccess) {
+            slot->key = hops; slot->n = n; slot->byPartition = byPartition; slot->epoch = in->bufferEpoch;
+            slot->subsOffset = subsOffset; slot->phaseStart = plan.phaseStart; slot->phaseDepth = depths;
+            slot->fourPath = fourPath; slot->maxWindow = maxWindow; slot->preOrder = preOrder;
+            slot->lastUse = ++in->planClock;
+        } else if (slot->dBlock != nullptr) {
+            slot->n = -1;
+        }
     }
     if (tmp != nullptr) { cudaStreamSynchronize(in->stream); cudaFree(tmp); }
     CUDA_OK(e);
@@ -608,6 +656,8 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 0);
     in->reorder = envInt("B200_REORDER", 1);
+    in->planCacheSize = std::max(0, std::min(16, envInt("B200_PLAN_CACHE", 4)));
+    in->planCache.reserve(16);
     in->thinR1 = envInt("B200_THIN_R1", 1);
     in->stackTail = envInt("B200_STACK_TAIL", 0);     // measured slower (0.458 vs 0.436 ms): off by default
     in->phaseT = envInt("B200_PHASE_T", 0);
@@ -755,6 +805,7 @@ int beagleSetTipStates(int instance, int tipIndex, const int* inStates) {
     CUDA_OK(cudaStreamSynchronize(in->stream));
     // the buffer is a compact tip from now on (states32[idx] != nullptr marks it; a previously assigned
     // partials slot stays reserved)
+    in->bufferEpoch++;
     return BEAGLE_SUCCESS;
 }
 
@@ -783,6 +834,7 @@ static int setPartialsImpl(Instance* in, int bufferIndex, const double* inPartia
         }
     CUDA_OK(cudaMemcpyAsync(dst, tmp.data(), sizeof(double) * in->partialsElems, cudaMemcpyHostToDevice, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
+    if (in->states32[bufferIndex] != nullptr) in->bufferEpoch++;      // tip -> partials: cached plans are stale
     in->states32[bufferIndex] = nullptr;
     in->states8[bufferIndex] = nullptr;
     return BEAGLE_SUCCESS;
@@ -882,6 +934,7 @@ int beagleSetPatternPartitions(int instance, int partitionCount, const int* inPa
         end[k] = p + 1;
     }
     for (int q = prev + 1; q < partitionCount; ++q) begin[q] = end[q] = in->P;
+    in->bufferEpoch++;
     in->partitionCount = partitionCount;
     in->partBegin = begin;
     in->partEnd = end;

@@ -48,6 +48,20 @@ struct alignas(16) Op4 {
 // one edge of a calculateEdgeDerivatives call
 struct EdgeRef { const double* post; const int* states; const double* pre; const double* D; };
 
+// a remembered execution plan: the caller's list (key) and its device-resident op records + subtree table
+struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; int kind = 0; };   // kind 1 = pre-order op
+struct CachedPlan {
+    std::vector<HostOp> key;
+    int n = -1;
+    bool byPartition = false, fourPath = false, preOrder = false;
+    unsigned long epoch = 0;
+    void* dBlock = nullptr;
+    size_t capacity = 0, subsOffset = 0;
+    std::vector<int> phaseStart, phaseDepth;
+    int maxWindow = 0;
+    long lastUse = 0;
+};
+
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
 
 struct Instance {
@@ -104,6 +118,10 @@ struct Instance {
     size_t walkSmemConfigured = 0, genericSmemConfigured = 0, mmaSmemConfigured = 0;
     int walkBlock = 128;
     int walkVariant = 0;
+    std::vector<CachedPlan> planCache;
+    int planCacheSize = 4;
+    long planClock = 0;
+    unsigned long bufferEpoch = 0;     // bumped whenever a buffer changes kind (tip <-> partials) or partitions change
     int reorder = 1;
     int thinR1 = 1;              // thin (latency-bound) phases of the 4-state walk use one pattern group per thread
     int stackTail = 0;           // operand stack for latency-bound (thin) phases of the 4-state walk (experiment, off)

@@ -454,3 +454,38 @@ def test_concurrent_instances_from_threads():
     [t.join() for t in threads]
     for k in range(4):
         assert len(results[k]) == 15 and all(v == serial[k] for v in results[k]), (k, serial[k], results[k][:3])
+
+
+def test_plan_cache_hits_and_invalidation():
+    """Identical op lists are served from the plan cache; a buffer changing kind (setTipStates / setPartials on a tip)
+    or different lists must not be.  Every value equals the cache-less engine."""
+    import os
+    tree, pats, model, site = H.synthetic_case(40, 300, 4, seed=77)
+
+    def run(cache):
+        os.environ["B200_PLAN_CACHE"] = cache
+        try:
+            d = _delegate(tree.copy(), pats, model, site, GPU, rescalingScheme=S_.NONE)
+        finally:
+            os.environ.pop("B200_PLAN_CACHE", None)
+        like = tdl.TreeDataLikelihood(d, d and tree)
+        out = []
+        for _ in range(4):                                  # same list, alternating parities -> cache hits
+            like.makeDirty()
+            out.append(like.getLogLikelihood())
+        like.updateNodeAndChildren(tree.tipCount + 3)       # a different (short) list
+        out.append(like.getLogLikelihood())
+        # tip 0 becomes a partials buffer (all-ones = missing data), then the full list again: the cached plan of
+        # that list would read stale compact states
+        d.beagle.setPartials(0, np.ones(pats.patternCount * 4 * site.getCategoryCount()))
+        like.makeDirty()
+        out.append(like.getLogLikelihood())
+        d.beagle.setTipStates(0, pats.states[0])
+        like.makeDirty()
+        out.append(like.getLogLikelihood())
+        d.finalize()
+        return out
+
+    a, b = run("4"), run("0")
+    assert a == b, (a, b)
+    assert a[0] == a[1] == a[2] == a[3] == a[6] and a[5] != a[0]
