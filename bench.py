@@ -475,19 +475,22 @@ def main():
             first = path[0][1]
             paths.append((ops, len(path), np.array([first + n], dtype=np.int32),
                           np.array([tree.branchLength(first) * 1.01]), np.array([tree.root + internal], dtype=np.int32)))
-        for ops, cnt, pidx, blen, rootIdx in paths[:8]:
-            inst.updateTransitionMatrices(0, pidx, None, None, blen, 1)
-            inst.updatePartials(ops, cnt, -1)
-            inst.calculateRootLogLikelihoods(rootIdx, ZERO, ZERO, MINUS1, 1, out)
-        t0 = time.perf_counter()
-        reps = 0
-        for _ in range(max(1, min(args.steps, 2000) // 64 + 1)):
-            for ops, cnt, pidx, blen, rootIdx in paths:
-                inst.updateTransitionMatrices(0, pidx, None, None, blen, 1)
-                inst.updatePartials(ops, cnt, -1)
-                inst.calculateRootLogLikelihoods(rootIdx, ZERO, ZERO, MINUS1, 1, out)
-                reps += 1
-        dt = time.perf_counter() - t0
+        def run_incremental(target, rounds):
+            for ops, cnt, pidx, blen, rootIdx in paths[:8]:
+                target.updateTransitionMatrices(0, pidx, None, None, blen, 1)
+                target.updatePartials(ops, cnt, -1)
+                target.calculateRootLogLikelihoods(rootIdx, ZERO, ZERO, MINUS1, 1, out)
+            t0 = time.perf_counter()
+            reps = 0
+            for _ in range(rounds):
+                for ops, cnt, pidx, blen, rootIdx in paths:
+                    target.updateTransitionMatrices(0, pidx, None, None, blen, 1)
+                    target.updatePartials(ops, cnt, -1)
+                    target.calculateRootLogLikelihoods(rootIdx, ZERO, ZERO, MINUS1, 1, out)
+                    reps += 1
+            return reps, time.perf_counter() - t0
+
+        reps, dt = run_incremental(inst, max(1, min(args.steps, 2000) // 64 + 1))
         inc = {"evals_per_s": reps / dt, "us_per_eval": 1e6 * dt / reps,
                "mean_ops_per_eval": float(np.mean([c for _, c, _, _, _ in paths])),
                "what": "one branch length changed: 1 matrix, tip-to-root path of partials ops, root; host buffers, synchronous"}
@@ -548,6 +551,13 @@ def main():
                                           f"oracle/beagle_cpu.c with {threads} pthreads (fastest of "
                                           f"{[t for t, _ in tried]})",
                                 "logL": cval, "rel_diff_vs_gpu": abs(cval - logL) / abs(cval)}
+        if inc is not None:
+            from oracle import cpu
+            cinst = create_instance(cpu.factory(threads=threads), evc, S, C, P, None)
+            issue_sync(cinst, evc, 0, out)
+            creps, cdt = run_incremental(cinst, 2)
+            cinst.finalize()
+            inc["cpu_port_evals_per_s"] = creps / cdt
     print(json.dumps(line), flush=True)
     inst.finalize()
     if world > 1:
