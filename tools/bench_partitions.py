@@ -51,7 +51,8 @@ for k in range(K):
     b.setStateFrequencies(k, models[k].getFrequencies())
     for node, t in branches:
         eig.append(k); rate.append(k); prob.append(node + k * n); lens.append(t)
-eig, rate, prob, lens = (np.array(x, dtype=np.int32) for x in (eig, rate, prob)) + (np.array(lens),)
+eig, rate, prob = (np.array(x, dtype=np.int32) for x in (eig, rate, prob))
+lens = np.array(lens)
 ops = []
 for node, c1, c2 in nodeOps:
     for k in range(K):
