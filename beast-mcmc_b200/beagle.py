@@ -161,6 +161,7 @@ _SIGNATURES = {
     "beagleCalculateRootLogLikelihoodsByPartition": ([_I, _IP, _IP, _IP, _IP, _IP, _I, _I, _DP, _DP], _I),
     "beagleGetSiteLogLikelihoods": ([_I, _DP], _I),
     "beagleCalculateEdgeDerivatives": ([_I, _IP, _IP, _IP, _IP, _I, _DP, _DP, _DP], _I),
+    "beagleCalculateCrossProductDerivative": ([_I, _IP, _IP, _IP, _IP, _DP, _I, _DP, _DP], _I),
     "b200SetKernelTiming": ([_I, _I], _I),
     "b200GetKernelTiming": ([_I, _I, _DP, C.POINTER(C.c_long)], _I),
     "b200HostAlloc": ([_L], C.c_void_p),
@@ -361,6 +362,17 @@ class BeagleJNIImpl(Beagle):
                                                              _ip(derivativeMatrixIndices)[1], _ip(categoryWeightsIndices)[1],
                                                              count, ptr(outDerivatives), ptr(outSumDerivatives),
                                                              ptr(outSumSquaredDerivatives)))
+
+    def calculateCrossProductDifferentials(self, postBufferIndices, preBufferIndices, categoryRatesIndices,
+                                           categoryWeightsIndices, edgeLengths, count, outSumDerivatives,
+                                           outSumSquaredDerivatives):
+        ptr = lambda a: None if a is None else a.ctypes.data_as(_DP)
+        lengths = np.ascontiguousarray(edgeLengths, dtype=np.float64)
+        self._check("calculateCrossProductDifferentials",
+                    self._lib.beagleCalculateCrossProductDerivative(
+                        self.instance, _ip(postBufferIndices)[1], _ip(preBufferIndices)[1], _ip(categoryRatesIndices)[1],
+                        _ip(categoryWeightsIndices)[1], lengths.ctypes.data_as(_DP), count, ptr(outSumDerivatives),
+                        ptr(outSumSquaredDerivatives)))
 
     def updatePartials(self, operations, operationCount, cumulativeScaleIndex):
         self._check("updatePartials", self._lib.beagleUpdatePartials(self.instance, _ip(operations)[1],

@@ -131,7 +131,7 @@ void destroyInstance(Instance* in) {
     cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dRates); cudaFree(in->dWeights);
     cudaFree(in->dFreqs); cudaFree(in->dScale); cudaFree(in->dPatternWeights);
     cudaFree(in->dPatternPartitions); cudaFree(in->dSite); cudaFree(in->dBlockSums); cudaFree(in->dOut);
-    cudaFree(in->dCounter); cudaFree(in->dStage);
+    cudaFree(in->dCounter); cudaFree(in->dStage); cudaFree(in->dScratch);
     if (in->hStage) cudaFreeHost(in->hStage);
     if (in->hOut) cudaFreeHost(in->hOut);
     for (int c = 0; c < T_CLASSES; ++c)
@@ -1331,6 +1331,56 @@ int beagleCalculateEdgeDerivatives(int instance, const int* postBufferIndices, c
         if (outSumSquaredDerivatives) outSumSquaredDerivatives[k] = host[count + k];
     }
     if (outDerivatives) memcpy(outDerivatives, host.data() + 2 * (size_t)count, sizeof(double) * (size_t)count * in->P);
+    return BEAGLE_SUCCESS;
+}
+
+// Beagle.calculateCrossProductDifferentials (SubstitutionModelCrossProductDelegate.java:158-176): S x S sums over the
+// listed branches, ADDED to outSumDerivatives (the caller zero-fills it first, :156,:169).
+int beagleCalculateCrossProductDerivative(int instance, const int* postBufferIndices, const int* preBufferIndices,
+                                          const int* categoryRatesIndices, const int* categoryWeightsIndices,
+                                          const double* edgeLengths, int count, double* outSumDerivatives,
+                                          double* outSumSquaredDerivatives) {
+    GET_INSTANCE(in, instance);
+    if (outSumSquaredDerivatives != nullptr) return BEAGLE_ERROR_NO_IMPLEMENTATION;   // BEAST passes null (:161,:175)
+    if (count <= 0) return BEAGLE_SUCCESS;
+    if (outSumDerivatives == nullptr || edgeLengths == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (!validRange(categoryRatesIndices[0], in->nSets) || !validRange(categoryWeightsIndices[0], in->nSets))
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    const size_t n = (size_t)in->S * in->S;
+    const size_t edgeDoubles = ((size_t)count * sizeof(EdgeRef) + 7) / 8;
+    const size_t need = edgeDoubles + ((size_t)crossProductBlocks(in, count) + 1) * n;
+    if (need > in->scratchDoubles) {
+        CUDA_OK(cudaStreamSynchronize(in->stream));
+        cudaFree(in->dScratch);
+        in->dScratch = nullptr; in->scratchDoubles = 0;
+        CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&in->dScratch), need * sizeof(double)));
+        in->scratchDoubles = need;
+    }
+    std::vector<EdgeRef> edges(count);
+    for (int e = 0; e < count; ++e) {
+        const int po = postBufferIndices[e], pr = preBufferIndices[e];
+        if (!validRange(po, in->nBuffers) || !validRange(pr, in->nBuffers) || in->partials[pr] == nullptr ||
+            (in->partials[po] == nullptr && in->states32[po] == nullptr))
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        edges[e].post = in->states32[po] != nullptr ? nullptr : in->partials[po];
+        edges[e].states = in->states32[po];
+        edges[e].pre = in->partials[pr];
+        edges[e].D = nullptr;
+        edges[e].len = edgeLengths[e];
+    }
+    EdgeRef* dEdges = reinterpret_cast<EdgeRef*>(in->dScratch);
+    double* work = in->dScratch + edgeDoubles;
+    CUDA_OK(cudaMemcpyAsync(dEdges, edges.data(), sizeof(EdgeRef) * count, cudaMemcpyHostToDevice, in->stream));
+    {
+        TimedScope ts(in, T_ROOT);
+        CUDA_OK(launchCrossProducts(in, dEdges, count, in->dRates + (size_t)categoryRatesIndices[0] * in->C,
+                                    in->dWeights + (size_t)categoryWeightsIndices[0] * in->C, work));
+    }
+    std::vector<double> host(n);
+    CUDA_OK(cudaMemcpyAsync(host.data(), work + (size_t)crossProductBlocks(in, count) * n, sizeof(double) * n,
+                            cudaMemcpyDeviceToHost, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
+    for (size_t q = 0; q < n; ++q) outSumDerivatives[q] += host[q];
     return BEAGLE_SUCCESS;
 }
 

@@ -46,7 +46,7 @@ struct alignas(16) Op4 {
 };
 
 // one edge of a calculateEdgeDerivatives call
-struct EdgeRef { const double* post; const int* states; const double* pre; const double* D; };
+struct EdgeRef { const double* post; const int* states; const double* pre; const double* D; double len; };
 
 // a remembered execution plan: the caller's list (key) and its device-resident op records + subtree table
 struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; int kind = 0; };   // kind 1 = pre-order op
@@ -98,6 +98,8 @@ struct Instance {
     double* dBlockSums = nullptr;
     double* dOut = nullptr;                   // [maxPartitions + 1]
     unsigned int* dCounter = nullptr;
+    double* dScratch = nullptr;               // grow-only workspace of the derivative calls
+    size_t scratchDoubles = 0;
     int partitionCount = 1;
     std::vector<int> partBegin, partEnd;      // contiguous pattern ranges per partition
     std::vector<int> hostPartitions;
@@ -143,6 +145,9 @@ cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nS
 cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow, bool preOrder);
 cudaError_t launchEdgeDerivatives(Instance* in, const EdgeRef* dEdges, int count, const double* weights, double* outPerPattern,
                                   double* outSum, double* outSumSq);
+int crossProductBlocks(const Instance* in, int count);
+cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, const double* rates,
+                                const double* weights, double* scratch);
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
                        const double* cumScale, int pBegin, int pEnd, double* dOutSlot);
 cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,

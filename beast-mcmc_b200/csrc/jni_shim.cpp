@@ -246,9 +246,13 @@ NATIVE(jint, calculateEdgeDifferentials)(JNIEnv* env, jobject, jint instance, ji
     DblOut o(env, out), s1(env, outSum), s2(env, outSumSquared);
     return beagleCalculateEdgeDerivatives(instance, a, b, c, w, count, o, s1, s2);
 }
-NATIVE(jint, calculateCrossProductDifferentials)(JNIEnv*, jobject, jint, jintArray, jintArray, jintArray, jintArray,
-                                                 jdoubleArray, jint, jdoubleArray, jdoubleArray) {
-    return BEAGLE_ERROR_NO_IMPLEMENTATION;
+NATIVE(jint, calculateCrossProductDifferentials)(JNIEnv* env, jobject, jint instance, jintArray post, jintArray pre,
+                                                 jintArray rates, jintArray weights, jdoubleArray lengths, jint count,
+                                                 jdoubleArray outSum, jdoubleArray outSumSquared) {
+    IntIn a(env, post), b(env, pre), r(env, rates), w(env, weights);
+    DblIn t(env, lengths);
+    DblOut s1(env, outSum), s2(env, outSumSquared);
+    return beagleCalculateCrossProductDerivative(instance, a, b, r, w, t, count, s1, s2);
 }
 NATIVE(jint, calculateEdgeDerivative)(JNIEnv*, jobject, jint, jintArray, jintArray, jint, jintArray, jintArray, jint, jint,
                                       jint, jintArray, jint, jdoubleArray, jdoubleArray) {

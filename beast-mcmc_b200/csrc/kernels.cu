@@ -1042,6 +1042,211 @@ cudaError_t launchEdgeDerivatives(Instance* in, const EdgeRef* dEdges, int count
 }
 
 // ---------------------------------------------------------------------------------------------
+// cross-product differentials (SubstitutionModelCrossProductDelegate.java:140-181 is the caller):
+//   out[i][j] += sum_edges t_e sum_p w_p ( sum_c weight_c rate_c pre_c[p][i] post_c[p][j] ) / ( sum_c weight_c pre_c[p].post_c[p] )
+// both partials sit at the child end of the branch, so sum_ij out[i][j] Q[i][j] = d logL / d(log of a common factor on
+// every branch length) exactly (the identity AbstractLogAdditiveSubstitutionModelGradient.java:220-227 relies on).
+// Two-stage and deterministic: every block leaves its S x S partial in `scratch`, k_cross_reduce adds them in a
+// fixed order.
+// ---------------------------------------------------------------------------------------------
+// 4-state: a thread owns a pattern, the 16 accumulators stay in registers across the block's edges.
+__global__ void __launch_bounds__(256)
+k_cross4(const EdgeRef* __restrict__ edges, int count, const double* __restrict__ rates,
+         const double* __restrict__ weights, const double* __restrict__ patternWeights, int C, int P, int Ppad,
+         double* __restrict__ scratch) {
+    __shared__ double red[8][16];
+    const int tid = threadIdx.x, p = blockIdx.x * 256 + tid;
+    double acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+    if (p < P) {
+        const double wp = patternWeights[p];
+        for (int e = blockIdx.y; e < count; e += gridDim.y) {
+            const EdgeRef r = edges[e];
+            const int s = r.states ? r.states[p] : -1;
+            double num[16], den = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) num[q] = 0.0;
+            for (int c = 0; c < C; ++c) {
+                const size_t off = ((size_t)c * Ppad + p) * 4;
+                double a[4], b[4];
+                ldg256(r.pre + off, a);
+                if (r.post) ldg256(r.post + off, b);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) b[j] = (s >= 4 || s == j) ? 1.0 : 0.0;
+                }
+                const double wc = weights[c], f = wc * rates[c];
+                den += wc * (a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double fa = f * a[i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) num[i * 4 + j] += fa * b[j];
+                }
+            }
+            const double sc = wp * r.len / den;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] += sc * num[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[tid >> 5][q] = v;
+    }
+    __syncthreads();
+    if (tid < 16) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][tid];
+        scratch[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + tid] = v;
+    }
+}
+
+// any state count: a block owns PCH patterns; per (edge, category) the scaled pre tile and the post tile go through
+// shared memory and every thread keeps a 4 x 4 tile of the S x S outer-product sum in registers.
+__global__ void __launch_bounds__(256)
+k_cross_generic(const EdgeRef* __restrict__ edges, int count, const double* __restrict__ rates,
+                const double* __restrict__ weights, const double* __restrict__ patternWeights, int S, int Sp, int C,
+                int P, int Ppad, int PCH, double* __restrict__ scratch) {
+    extern __shared__ double smx[];
+    const int S4 = (S + 3) & ~3, nt = S4 / 4, ntiles = nt * nt;
+    double* fp = smx;                       // [PCH]  w_p t_e / den_p
+    double* spre = smx + PCH;               // [PCH][S4]
+    double* spost = spre + (size_t)PCH * S4;
+    const int tid = threadIdx.x, p0 = blockIdx.x * PCH, np = min(PCH, P - p0);
+    double* mine = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * S * S;
+    for (int tb = 0; tb < ntiles; tb += 256) {
+        const int tile = tb + tid;
+        const bool active = tile < ntiles;
+        const int ti = active ? tile / nt : 0, tj = active ? tile % nt : 0;
+        double acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+        for (int e = blockIdx.y; e < count; e += gridDim.y) {
+            const EdgeRef r = edges[e];
+            {   // den_p: 8 lanes per pattern, fixed-order shuffle reduction
+                const int pp = tid >> 3, lane = tid & 7;
+                for (int base = 0; base < np; base += 32) {
+                    const int q = base + pp;
+                    double d = 0.0;
+                    if (q < np) {
+                        const int p = p0 + q;
+                        const int s = r.states ? r.states[p] : -1;
+                        for (int c = 0; c < C; ++c) {
+                            const double* pre = r.pre + ((size_t)c * Ppad + p) * Sp;
+                            double dc = 0.0;
+                            if (r.post) {
+                                const double* post = r.post + ((size_t)c * Ppad + p) * Sp;
+                                for (int k = lane; k < S; k += 8) dc += pre[k] * post[k];
+                            } else if (s < S) {
+                                if (lane == (s & 7)) dc = pre[s];
+                            } else {
+                                for (int k = lane; k < S; k += 8) dc += pre[k];
+                            }
+                            d += weights[c] * dc;
+                        }
+                    }
+                    d += __shfl_xor_sync(0xffffffffu, d, 4);
+                    d += __shfl_xor_sync(0xffffffffu, d, 2);
+                    d += __shfl_xor_sync(0xffffffffu, d, 1);
+                    if (q < np && lane == 0) fp[q] = patternWeights[p0 + q] * r.len / d;
+                }
+            }
+            __syncthreads();
+            for (int c = 0; c < C; ++c) {
+                const double f = weights[c] * rates[c];
+                for (int idx = tid; idx < np * S4; idx += 256) {
+                    const int pp = idx / S4, k = idx - pp * S4, p = p0 + pp;
+                    double a = 0.0, b = 0.0;
+                    if (k < S) {
+                        a = r.pre[((size_t)c * Ppad + p) * Sp + k] * fp[pp] * f;
+                        if (r.post) b = r.post[((size_t)c * Ppad + p) * Sp + k];
+                        else { const int s = r.states[p]; b = (s >= S || s == k) ? 1.0 : 0.0; }
+                    }
+                    spre[idx] = a;
+                    spost[idx] = b;
+                }
+                __syncthreads();
+                if (active) {
+                    for (int pp = 0; pp < np; ++pp) {
+                        const double2* pa = reinterpret_cast<const double2*>(spre + (size_t)pp * S4 + ti * 4);
+                        const double2* pb = reinterpret_cast<const double2*>(spost + (size_t)pp * S4 + tj * 4);
+                        const double2 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+                        const double a[4] = {a0.x, a0.y, a1.x, a1.y}, b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * b[y];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int i = ti * 4 + x, j = tj * 4 + y;
+                    if (i < S && j < S) mine[(size_t)i * S + j] = acc[x][y];
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_cross_reduce(const double* __restrict__ scratch, int nBlocks, int n, double* __restrict__ out) {
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= n) return;
+    double v = 0.0;
+    for (int b = 0; b < nBlocks; ++b) v += scratch[(size_t)b * n + q];
+    out[q] = v;
+}
+
+// scratch must hold crossProductBlocks() * S * S + S * S doubles; the result lands in the last S * S.
+int crossProductBlocks(const Instance* in, int count) {
+    const bool four = in->Sp == 4;
+    const int pch = four ? 256 : std::max(1, std::min(32, 2048 / in->S));
+    const int chunks = (in->P + pch - 1) / pch;
+    const int groups = std::max(1, std::min(count, (2 * in->smCount + chunks - 1) / chunks));
+    return chunks * groups;
+}
+
+cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, const double* rates,
+                                const double* weights, double* scratch) {
+    const bool four = in->Sp == 4;
+    const int pch = four ? 256 : std::max(1, std::min(32, 2048 / in->S));
+    const int chunks = (in->P + pch - 1) / pch;
+    const int groups = std::max(1, std::min(count, (2 * in->smCount + chunks - 1) / chunks));
+    const int n = in->S * in->S;
+    dim3 grid(chunks, groups);
+    if (four) {
+        k_cross4<<<grid, 256, 0, in->stream>>>(dEdges, count, rates, weights, in->dPatternWeights, in->C, in->P,
+                                               in->Ppad, scratch);
+    } else {
+        const int S4 = (in->S + 3) & ~3;
+        const size_t smem = sizeof(double) * ((size_t)pch + 2 * (size_t)pch * S4);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_cross_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_cross_generic<<<grid, 256, smem, in->stream>>>(dEdges, count, rates, weights, in->dPatternWeights, in->S,
+                                                         in->Sp, in->C, in->P, in->Ppad, pch, scratch);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_cross_reduce<<<(n + 255) / 256, 256, 0, in->stream>>>(scratch, chunks * groups, n,
+                                                            scratch + (size_t)chunks * groups * n);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // root integration + reduction
 // ---------------------------------------------------------------------------------------------
 // site[p] = log(sum_i pi_i (sum_c w_c root[c,p,i])) + cum[p]   (GeneralLikelihoodCore.java:358-408)

@@ -626,3 +626,24 @@ class DiscreteTraitBranchRateDelegate:
         self.beagle.calculateEdgeDifferentials(post, pre, der, np.zeros(1, dtype=np.int32), len(nodes), None,
                                                first, firstSquared)
         return first
+
+
+class SubstitutionModelCrossProductDelegate(DiscreteTraitBranchRateDelegate):
+    """discrete/SubstitutionModelCrossProductDelegate.java:85-181 (coverWholeTree + getNodeDerivatives) for a single
+    substitution model: the S x S cross-product differentials of the whole tree, the input of
+    AbstractLogAdditiveSubstitutionModelGradient.java:239-270."""
+
+    def getBranchLength(self, node: int) -> float:
+        return self.tree.branchLength(node)
+
+    def getCrossProducts(self) -> np.ndarray:
+        tree, d = self.tree, self.likelihoodDelegate
+        self.simulate()
+        nodes = [n for n in range(tree.nodeCount) if n != tree.root]
+        post = np.asarray([d.getPartialBufferIndex(n) for n in nodes], dtype=np.int32)
+        pre = np.asarray([self.getPreOrderPartialIndex(n) for n in nodes], dtype=np.int32)
+        lengths = np.asarray([self.getBranchLength(n) for n in nodes], dtype=np.float64)
+        first = np.zeros(d.stateCount * d.stateCount)
+        zero = np.zeros(1, dtype=np.int32)
+        self.beagle.calculateCrossProductDifferentials(post, pre, zero, zero, lengths, len(nodes), first, None)
+        return first.reshape(d.stateCount, d.stateCount)

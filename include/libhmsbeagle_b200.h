@@ -283,6 +283,16 @@ BEAGLE_DLLEXPORT int beagleCalculateRootLogLikelihoodsByPartition(
     int instance, const int* bufferIndices, const int* categoryWeightsIndices, const int* stateFrequenciesIndices,
     const int* cumulativeScaleIndices, const int* partitionIndices, int partitionCount, int count,
     double* outSumLogLikelihoodByPartition, double* outSumLogLikelihood);
+/* Beagle.calculateCrossProductDifferentials(post[], pre[], {ratesIdx}, {weightsIdx}, edgeLengths[], count, outSum,
+ * outSumSquared) (discrete/SubstitutionModelCrossProductDelegate.java:158-176; consumed by
+ * AbstractLogAdditiveSubstitutionModelGradient.java:239-270): outSum is S*S row-major and is ADDED to:
+ *   outSum[i*S+j] += sum_e t_e sum_p weight_p (sum_c w_c r_c pre_e[c,p,i] post_e[c,p,j]) / (sum_c w_c pre_e[c,p,.].post_e[c,p,.])
+ * outSumSquared must be NULL (BEAST passes null). */
+BEAGLE_DLLEXPORT int beagleCalculateCrossProductDerivative(int instance, const int* postBufferIndices,
+                                                           const int* preBufferIndices, const int* categoryRatesIndices,
+                                                           const int* categoryWeightsIndices, const double* edgeLengths,
+                                                           int count, double* outSumDerivatives,
+                                                           double* outSumSquaredDerivatives);
 /* Beagle.calculateEdgeDifferentials(post[], pre[], derivativeMatrix[], {weightsIdx}, count, out, outSum, outSumSquared)
  * (preorder/AbstractBeagleBranchGradientDelegate.java:83-91): per edge e and pattern p
  *   d[e,p] = (sum_c w_c sum_j pre[c,p,j] sum_k D[c,j,k] post[c,p,k]) / (sum_c w_c sum_j pre[c,p,j] post[c,p,j]);

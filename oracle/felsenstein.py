@@ -309,6 +309,30 @@ class OracleBeagle:
             if outSumSquaredDerivatives is not None:
                 outSumSquaredDerivatives[e] = float(np.dot(self.patternWeights, d * d))
 
+    def calculateCrossProductDifferentials(self, postBufferIndices, preBufferIndices, categoryRatesIndices,
+                                           categoryWeightsIndices, edgeLengths, count, outSumDerivatives,
+                                           outSumSquaredDerivatives):
+        """Call site: SubstitutionModelCrossProductDelegate.java:158-176.  The arithmetic is beagle-lib's (4.0.x,
+        not vendored in the reference tree): per branch, pattern and category the outer product of the pre-order and
+        post-order partials at the child end of the branch, weighted by weight_c * rate_c * t and divided by the
+        pattern likelihood, summed into an S x S array that is ADDED to ``outSumDerivatives``.  Pinned here by the
+        identity sum_ij out[ij] Q[ij] = d logL / d log(branch-length factor) (tests/test_preorder_oracle.py), which is
+        how AbstractLogAdditiveSubstitutionModelGradient.java:220-227 consumes it."""
+        assert outSumSquaredDerivatives is None
+        w = self.categoryWeights[categoryWeightsIndices[0]]
+        r = self.categoryRates[categoryRatesIndices[0]]
+        acc = np.zeros((self.S, self.S))
+        for e in range(count):
+            post = self._post_as_partials(postBufferIndices[e])
+            pre = self.partials[preBufferIndices[e]]
+            den = np.zeros(self.P)
+            num = np.zeros((self.P, self.S, self.S))
+            for c in range(self.C):
+                den += w[c] * (pre[c] * post[c]).sum(axis=1)
+                num += w[c] * r[c] * pre[c][:, :, None] * post[c][:, None, :]
+            acc += edgeLengths[e] * np.einsum("p,pij->ij", self.patternWeights / den, num)
+        outSumDerivatives[:self.S * self.S] += acc.reshape(-1)
+
     # ---- scale factors ------------------------------------------------------------------
     def _logf(self, idx):
         return self.scale[idx] if self.log_scalers else np.log(self.scale[idx])

@@ -68,6 +68,9 @@ def test_primates_ambiguity_partials():
 @pytest.mark.parametrize("tips,patterns,cats,states", [
     (8, 33, 1, 4), (50, 257, 4, 4), (50, 1000, 2, 4), (33, 500, 5, 4), (20, 300, 8, 4), (12, 100, 13, 4),
     (16, 200, 1, 20), (16, 130, 4, 20), (10, 96, 1, 61), (9, 70, 2, 61), (12, 64, 3, 7), (6, 40, 1, 2),
+    (10, 64, 40, 4),       # more than 32 categories: 4-state data on the generic block walk
+    (6, 40, 1, 70),        # state count without a tensor-path template instance (FMA block walk)
+    (7, 48, 2, 30),        # NT = 4 tensor path
 ])
 @pytest.mark.parametrize("scheme", [S_.NONE, S_.ALWAYS])
 def test_oracle_parity(tips, patterns, cats, states, scheme):
