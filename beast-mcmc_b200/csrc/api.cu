@@ -1290,6 +1290,19 @@ int beagleGetSiteLogLikelihoods(int instance, double* outLogLikelihoods) {
 }
 
 // ---- edge derivatives (pre-order route) ---------------------------------------------------------
+// grow-only device workspace of the derivative calls (stream-ordered users only)
+static cudaError_t ensureScratch(Instance* in, size_t doubles) {
+    if (doubles <= in->scratchDoubles) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(in->stream);
+    if (e != cudaSuccess) return e;
+    cudaFree(in->dScratch);
+    in->dScratch = nullptr;
+    in->scratchDoubles = 0;
+    e = cudaMalloc(reinterpret_cast<void**>(&in->dScratch), doubles * sizeof(double));
+    if (e == cudaSuccess) in->scratchDoubles = doubles;
+    return e;
+}
+
 int beagleCalculateEdgeDerivatives(int instance, const int* postBufferIndices, const int* preBufferIndices,
                                    const int* derivativeMatrixIndices, const int* categoryWeightsIndices, int count,
                                    double* outDerivatives, double* outSumDerivatives, double* outSumSquaredDerivatives) {
@@ -1306,26 +1319,26 @@ int beagleCalculateEdgeDerivatives(int instance, const int* postBufferIndices, c
         edges[e].states = in->states32[po];
         edges[e].pre = in->partials[pr];
         edges[e].D = in->dMat + (size_t)dm * in->matStride;
+        edges[e].len = 0.0;
     }
-    void* dEdges = nullptr;
-    double* dOut = nullptr;
+    // workspace: [edge records][sum, sumSquared per edge][per-pattern values (optional)][tile partials (tensor form)]
     const size_t perEdge = outDerivatives != nullptr ? (size_t)in->P : 0;
-    CUDA_OK(cudaMalloc(&dEdges, sizeof(EdgeRef) * count));
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dOut), sizeof(double) * ((size_t)count * (2 + perEdge)));
-    if (e != cudaSuccess) { cudaFree(dEdges); CUDA_OK(e); }
-    e = cudaMemcpyAsync(dEdges, edges.data(), sizeof(EdgeRef) * count, cudaMemcpyHostToDevice, in->stream);
-    if (e == cudaSuccess) {
+    const size_t edgeDoubles = ((size_t)count * sizeof(EdgeRef) + 7) / 8;
+    const size_t results = (size_t)count * (2 + perEdge);
+    const size_t partials = edgeDerivativeWorkspace(in, count);
+    CUDA_OK(ensureScratch(in, edgeDoubles + results + partials));
+    EdgeRef* dEdges = reinterpret_cast<EdgeRef*>(in->dScratch);
+    double* dOut = in->dScratch + edgeDoubles;
+    CUDA_OK(cudaMemcpyAsync(dEdges, edges.data(), sizeof(EdgeRef) * count, cudaMemcpyHostToDevice, in->stream));
+    {
         TimedScope ts(in, T_ROOT);
-        e = launchEdgeDerivatives(in, static_cast<const EdgeRef*>(dEdges), count,
-                                  in->dWeights + (size_t)categoryWeightsIndices[0] * in->C,
-                                  perEdge ? dOut + 2 * (size_t)count : nullptr, dOut, dOut + count);
+        CUDA_OK(launchEdgeDerivatives(in, dEdges, count, in->dWeights + (size_t)categoryWeightsIndices[0] * in->C,
+                                      perEdge ? dOut + 2 * (size_t)count : nullptr, dOut, dOut + count,
+                                      partials ? dOut + results : nullptr));
     }
-    std::vector<double> host((size_t)count * (2 + perEdge));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), dOut, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, in->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(in->stream);
-    cudaFree(dEdges);
-    cudaFree(dOut);
-    CUDA_OK(e);
+    std::vector<double> host(results);
+    CUDA_OK(cudaMemcpyAsync(host.data(), dOut, sizeof(double) * results, cudaMemcpyDeviceToHost, in->stream));
+    CUDA_OK(cudaStreamSynchronize(in->stream));
     for (int k = 0; k < count; ++k) {
         if (outSumDerivatives) outSumDerivatives[k] = host[k];
         if (outSumSquaredDerivatives) outSumSquaredDerivatives[k] = host[count + k];
@@ -1349,13 +1362,7 @@ int beagleCalculateCrossProductDerivative(int instance, const int* postBufferInd
     const size_t n = (size_t)in->S * in->S;
     const size_t edgeDoubles = ((size_t)count * sizeof(EdgeRef) + 7) / 8;
     const size_t need = edgeDoubles + ((size_t)crossProductBlocks(in, count) + 1) * n;
-    if (need > in->scratchDoubles) {
-        CUDA_OK(cudaStreamSynchronize(in->stream));
-        cudaFree(in->dScratch);
-        in->dScratch = nullptr; in->scratchDoubles = 0;
-        CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&in->dScratch), need * sizeof(double)));
-        in->scratchDoubles = need;
-    }
+    CUDA_OK(ensureScratch(in, need));
     std::vector<EdgeRef> edges(count);
     for (int e = 0; e < count; ++e) {
         const int po = postBufferIndices[e], pr = preBufferIndices[e];

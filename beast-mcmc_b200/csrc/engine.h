@@ -117,7 +117,7 @@ struct Instance {
     long timedLaunches[T_CLASSES] = {0, 0, 0};
 
     // tuning knobs (environment overridable, see api.cu)
-    size_t walkSmemConfigured = 0, genericSmemConfigured = 0, mmaSmemConfigured = 0;
+    size_t walkSmemConfigured = 0, genericSmemConfigured = 0, mmaSmemConfigured[2] = {0, 0};
     int walkBlock = 128;
     int walkVariant = 0;
     std::vector<CachedPlan> planCache;
@@ -143,8 +143,10 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
 // dSubs[k] = (first op, one-past-last op, first pattern, one-past-last pattern) of subtree walk k
 cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder);
 cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow, bool preOrder);
+// `partial`: edgeDerivativeWorkspace() doubles when that is non-zero (tensor-pipe form), else nullptr
+size_t edgeDerivativeWorkspace(const Instance* in, int count);
 cudaError_t launchEdgeDerivatives(Instance* in, const EdgeRef* dEdges, int count, const double* weights, double* outPerPattern,
-                                  double* outSum, double* outSumSq);
+                                  double* outSum, double* outSumSq, double* partial);
 int crossProductBlocks(const Instance* in, int count);
 cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, const double* rates,
                                 const double* weights, double* scratch);

@@ -753,7 +753,7 @@ __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
 
 // Block = WARPS warps x 16 patterns.  The two matrices of the NEXT (op, category) pair are fetched with
 // cp.async (LDGSTS) into the other half of a double buffer while the tensor pipe works on the current pair.
-template <int NT, int WARPS, bool DB>
+template <int NT, int WARPS, bool DB, bool PRE>
 __global__ void __launch_bounds__(WARPS * 32)
 k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int C, int Ppad, int logScalers) {
     constexpr int Sp = 8 * NT;
@@ -772,7 +772,8 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
     auto stageAsync = [&](int flat, int buf) {
         const DevOp* o = ops + range.x + flat / C;
         const int c = flat % C;
-        const double* g1 = o->m1 + mRow + (size_t)c * Sp * Sp;
+        // pre-order ops contract over the ROW index of the node's own matrix: stage its transposed copy (first half)
+        const double* g1 = o->m1 + (PRE ? 0 : mRow) + (size_t)c * Sp * Sp;
         const double* g2 = o->m2 + mRow + (size_t)c * Sp * Sp;
         double* s1 = smm + (size_t)buf * 2 * MATSZ;
         double* s2 = s1 + MATSZ;
@@ -814,6 +815,76 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
             }
         }
         double acc[2][NT][2];
+        if constexpr (PRE) {
+            // pre[node][j] = sum_i ( pre[parent][i] * (M_sib post[sib])[i] ) M_node[i][j]
+            // (1) v = M_sib post[sib] on the tensor pipe (or a column lookup for a compact tip)
+            double u[2][NT][2];
+            if (op.c2 != nullptr) {
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) { u[m][n][0] = 0.0; u[m][n][1] = 0.0; }
+                const double* xrow0 = op.c2 + ((size_t)c * Ppad + (pw + g)) * Sp + t;
+                const double* xrow1 = xrow0 + (size_t)8 * Sp;
+                const double* brow = P2 + g * LD + t;
+#pragma unroll 4
+                for (int kc = 0; kc < Sp / 4; ++kc) {
+                    double a0 = 0.0, a1 = 0.0;
+                    if (act[0]) a0 = xrow0[4 * kc];
+                    if (act[1]) a1 = xrow1[4 * kc];
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        const double b = brow[n * 8 * LD + 4 * kc];
+                        dmma884acc(u[0][n][0], u[0][n][1], a0, b);
+                        dmma884acc(u[1][n][0], u[1][n][1], a1, b);
+                    }
+                }
+            } else {
+                const int* st = static_cast<const int*>(op.s2);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int s = act[m] ? st[pw + 8 * m + g] : S;
+#pragma unroll
+                    for (int n = 0; n < NT; ++n)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int i = 8 * n + 2 * t + e;
+                            u[m][n][e] = (s < S) ? P2[i * LD + s] : ((i < S) ? 1.0 : 0.0);
+                        }
+                }
+            }
+            // (2) times the parent's pre-order partial, read in the accumulator layout
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const double* prow = op.c1 + ((size_t)c * Ppad + (pw + 8 * m + g)) * Sp + 2 * t;
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (act[m]) v = *reinterpret_cast<const double2*>(prow + 8 * n);
+                    u[m][n][0] *= v.x; u[m][n][1] *= v.y;
+                    acc[m][n][0] = 0.0; acc[m][n][1] = 0.0;
+                }
+            }
+            // (3) second contraction.  The sum over i may visit the states in any order, so k-chunk (n, e0) is
+            // DEFINED as the four states lane t already holds: i = 8n + 2t + (e0 ^ (t >> 1)) -- no accumulator ->
+            // A-fragment shuffle, and with the (Sp+4) row stride the B reads stay bank-conflict free.
+            const int flip = t >> 1;
+            const double* brow = P1 + g * LD + 2 * t;
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int e0 = 0; e0 < 2; ++e0) {
+                    const int e = e0 ^ flip;
+                    const double a0 = e ? u[0][n][1] : u[0][n][0];
+                    const double a1 = e ? u[1][n][1] : u[1][n][0];
+#pragma unroll
+                    for (int n2 = 0; n2 < NT; ++n2) {
+                        const double b = brow[n2 * 8 * LD + 8 * n + e];
+                        dmma884acc(acc[0][n2][0], acc[0][n2][1], a0, b);
+                        dmma884acc(acc[1][n2][0], acc[1][n2][1], a1, b);
+                    }
+                }
+        } else {
 #pragma unroll
         for (int child = 0; child < 2; ++child) {
             const double* xg = child == 0 ? op.c1 : op.c2;
@@ -861,6 +932,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
 #pragma unroll
                     for (int e = 0; e < 2; ++e)
                         acc[m][n][e] = child == 0 ? cur[m][n][e] : acc[m][n][e] * cur[m][n][e];
+        }
         }
         // store the (unscaled) tile: lane (g,t) owns states 8n+2t, 8n+2t+1 of rows g and g+8
 #pragma unroll
@@ -915,29 +987,38 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
     }
 }
 
-template <int NT, int WARPS, bool DB = false>
+template <int NT, int WARPS, bool PRE = false, bool DB = false>
 static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     constexpr int Sp = 8 * NT;
     const size_t smem = (DB ? 4 : 2) * (size_t)Sp * (Sp + 4) * sizeof(double);
-    if (smem > in->mmaSmemConfigured) {
-        cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > in->mmaSmemConfigured[PRE ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, DB, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        in->mmaSmemConfigured = smem;
+        in->mmaSmemConfigured[PRE ? 1 : 0] = smem;
     }
     dim3 grid((maxWindow + WARPS * 16 - 1) / (WARPS * 16), nSubs);
-    k_walk_mma<NT, WARPS, DB><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
+    k_walk_mma<NT, WARPS, DB, PRE><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
     return cudaGetLastError();
 }
 
 cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow, bool preOrder) {
     if (nSubs <= 0) return cudaSuccess;
-    if (in->genericMma && !preOrder) {
+    if (in->genericMma && preOrder) {
+        switch (in->Sp / 8) {
+            case 1: return launchWalkMmaT<1, 4, true>(in, dOps, dSubs, nSubs, maxWindow);
+            case 2: return launchWalkMmaT<2, 4, true>(in, dOps, dSubs, nSubs, maxWindow);
+            case 3: return launchWalkMmaT<3, 4, true>(in, dOps, dSubs, nSubs, maxWindow);
+            case 4: return launchWalkMmaT<4, 4, true>(in, dOps, dSubs, nSubs, maxWindow);
+            case 8: return launchWalkMmaT<8, 4, true>(in, dOps, dSubs, nSubs, maxWindow);
+            default: break;
+        }
+    } else if (in->genericMma) {
         switch (in->Sp / 8) {
             case 1: return launchWalkMmaT<1, 4>(in, dOps, dSubs, nSubs, maxWindow);
             case 2: return launchWalkMmaT<2, 4>(in, dOps, dSubs, nSubs, maxWindow);
             case 3: return launchWalkMmaT<3, 4>(in, dOps, dSubs, nSubs, maxWindow);
             case 4: return launchWalkMmaT<4, 4>(in, dOps, dSubs, nSubs, maxWindow);
-            case 8: return in->mmaWarps == 8 ? launchWalkMmaT<8, 8, true>(in, dOps, dSubs, nSubs, maxWindow) : launchWalkMmaT<8, 4>(in, dOps, dSubs, nSubs, maxWindow);
+            case 8: return in->mmaWarps == 8 ? launchWalkMmaT<8, 8, false, true>(in, dOps, dSubs, nSubs, maxWindow) : launchWalkMmaT<8, 4>(in, dOps, dSubs, nSubs, maxWindow);
             default: break;      // other state counts: FMA block walk below
         }
     }
@@ -1026,8 +1107,172 @@ k_edge_derivatives(const EdgeRef* __restrict__ edges, const double* __restrict__
     if (tid == 0) { outSum[blockIdx.x] = red1[0]; outSumSq[blockIdx.x] = red2[0]; }
 }
 
+// Tensor-pipe form for the state counts of the DMMA walk (Sp = 8 NT): block = 4 warps x 16 patterns of ONE edge.
+// Per category the row-major D_c is staged like a transition matrix, v = D_c post is the same m8n8k4 contraction as a
+// post-order child term, and the two dot products with the pre-order partial are taken in the accumulator layout.
+// Block partial sums go to `partial[(edge * tiles + tile) * 2 + {0,1}]`; k_edge_sum adds them in tile order.
+template <int NT>
+__global__ void __launch_bounds__(128)
+k_edge_derivatives_mma(const EdgeRef* __restrict__ edges, const double* __restrict__ weights,
+                       const double* __restrict__ patternWeights, int S, int C, int P, int Ppad,
+                       double* __restrict__ outPerPattern, double* __restrict__ partial) {
+    constexpr int Sp = 8 * NT;
+    constexpr int LD = Sp + 4;
+    extern __shared__ double smm[];                  // [Sp][LD]
+    __shared__ double red[4][2];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const EdgeRef e = edges[blockIdx.y];
+    const int pw = blockIdx.x * 64 + w * 16;
+    const size_t mRow = (size_t)C * Sp * Sp;
+    bool act[2];
+    int st[2] = {0, 0};
+    double num[2] = {0.0, 0.0}, den[2] = {0.0, 0.0};
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        act[m] = pw + 8 * m + g < P;
+        if (e.states != nullptr && act[m]) st[m] = e.states[pw + 8 * m + g];
+    }
+    for (int c = 0; c < C; ++c) {
+        __syncthreads();                             // everyone is done with the previous category's matrix
+        const double* gD = e.D + mRow + (size_t)c * Sp * Sp;
+        for (int q = tid; q < Sp * Sp / 2; q += 128) {
+            const int i = (2 * q) / Sp, j = (2 * q) % Sp;
+            cpAsync16(smm + i * LD + j, gD + 2 * q);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        double v[2][NT][2];
+        if (e.post != nullptr) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) { v[m][n][0] = 0.0; v[m][n][1] = 0.0; }
+            const double* xrow0 = e.post + ((size_t)c * Ppad + (pw + g)) * Sp + t;
+            const double* xrow1 = xrow0 + (size_t)8 * Sp;
+            const double* brow = smm + g * LD + t;
+#pragma unroll 4
+            for (int kc = 0; kc < Sp / 4; ++kc) {
+                double a0 = 0.0, a1 = 0.0;
+                if (act[0]) a0 = xrow0[4 * kc];
+                if (act[1]) a1 = xrow1[4 * kc];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const double b = brow[n * 8 * LD + 4 * kc];
+                    dmma884acc(v[0][n][0], v[0][n][1], a0, b);
+                    dmma884acc(v[1][n][0], v[1][n][1], a1, b);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int x = 0; x < 2; ++x) {
+                        const int i = 8 * n + 2 * t + x;
+                        double d = 0.0;
+                        if (st[m] < S) d = smm[i * LD + st[m]];
+                        else for (int k = 0; k < S; ++k) d += smm[i * LD + k];
+                        v[m][n][x] = d;
+                    }
+        }
+        const double wc = weights[c];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            if (!act[m]) continue;
+            const size_t off = ((size_t)c * Ppad + (pw + 8 * m + g)) * Sp + 2 * t;
+            double nn = 0.0, dd = 0.0;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const double2 a = *reinterpret_cast<const double2*>(e.pre + off + 8 * n);
+                nn += a.x * v[m][n][0] + a.y * v[m][n][1];
+                if (e.post != nullptr) {
+                    const double2 b = *reinterpret_cast<const double2*>(e.post + off + 8 * n);
+                    dd += a.x * b.x + a.y * b.y;
+                } else {
+                    const int i = 8 * n + 2 * t;
+                    if (st[m] >= S) dd += (i < S ? a.x : 0.0) + (i + 1 < S ? a.y : 0.0);
+                    else dd += (i == st[m] ? a.x : 0.0) + (i + 1 == st[m] ? a.y : 0.0);
+                }
+            }
+            num[m] += wc * nn;
+            den[m] += wc * dd;
+        }
+    }
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        double nn = num[m], dd = den[m];
+        nn += __shfl_xor_sync(0xffffffffu, nn, 1); nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 1); dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+        if (act[m] && t == 0) {
+            const int p = pw + 8 * m + g;
+            const double d = nn / dd;
+            if (outPerPattern) outPerPattern[(size_t)blockIdx.y * P + p] = d;
+            s1 += patternWeights[p] * d;
+            s2 += patternWeights[p] * d * d;
+        }
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) { red[w][0] = s1; red[w][1] = s2; }
+    __syncthreads();
+    if (tid < 2) {
+        const double r = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + tid] = r;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_edge_sum(const double* __restrict__ partial, int tiles, int count, double* __restrict__ outSum,
+           double* __restrict__ outSumSq) {
+    const int e = blockIdx.x * 128 + threadIdx.x;
+    if (e >= count) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < tiles; ++k) { s1 += partial[((size_t)e * tiles + k) * 2]; s2 += partial[((size_t)e * tiles + k) * 2 + 1]; }
+    outSum[e] = s1;
+    outSumSq[e] = s2;
+}
+
+template <int NT>
+static cudaError_t launchEdgeMmaT(Instance* in, const EdgeRef* dEdges, int count, const double* weights,
+                                  double* outPerPattern, double* outSum, double* outSumSq, double* partial) {
+    constexpr int Sp = 8 * NT;
+    const size_t smem = (size_t)Sp * (Sp + 4) * sizeof(double);
+    const int tiles = (in->P + 63) / 64;
+    dim3 grid(tiles, count);
+    k_edge_derivatives_mma<NT><<<grid, 128, smem, in->stream>>>(dEdges, weights, in->dPatternWeights, in->S, in->C,
+                                                                in->P, in->Ppad, outPerPattern, partial);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_edge_sum<<<(count + 127) / 128, 128, 0, in->stream>>>(partial, tiles, count, outSum, outSumSq);
+    return cudaGetLastError();
+}
+
+// doubles of workspace the tensor-pipe form needs (0 = this state count uses the plain kernel)
+size_t edgeDerivativeWorkspace(const Instance* in, int count) {
+    const int nt = in->Sp / 8;
+    const bool mma = in->genericMma && in->matCP == 0 && in->Sp % 8 == 0 && (nt >= 1 && nt <= 4 || nt == 8) && count <= 65535;
+    return mma ? (size_t)count * ((in->P + 63) / 64) * 2 : 0;
+}
+
 cudaError_t launchEdgeDerivatives(Instance* in, const EdgeRef* dEdges, int count, const double* weights,
-                                  double* outPerPattern, double* outSum, double* outSumSq) {
+                                  double* outPerPattern, double* outSum, double* outSumSq, double* partial) {
+    if (partial != nullptr) {
+        switch (in->Sp / 8) {
+            case 1: return launchEdgeMmaT<1>(in, dEdges, count, weights, outPerPattern, outSum, outSumSq, partial);
+            case 2: return launchEdgeMmaT<2>(in, dEdges, count, weights, outPerPattern, outSum, outSumSq, partial);
+            case 3: return launchEdgeMmaT<3>(in, dEdges, count, weights, outPerPattern, outSum, outSumSq, partial);
+            case 4: return launchEdgeMmaT<4>(in, dEdges, count, weights, outPerPattern, outSum, outSumSq, partial);
+            case 8: return launchEdgeMmaT<8>(in, dEdges, count, weights, outPerPattern, outSum, outSumSq, partial);
+            default: break;
+        }
+    }
     const size_t need = (size_t)in->C * in->S * in->S * sizeof(double);
     const size_t budget = in->maxSmemOptin > 16384 ? in->maxSmemOptin - 8192 : 40000;
     const int stageD = need <= budget ? 1 : 0;
@@ -1115,7 +1360,7 @@ k_cross_generic(const EdgeRef* __restrict__ edges, int count, const double* __re
     extern __shared__ double smx[];
     const int S4 = (S + 3) & ~3, nt = S4 / 4, ntiles = nt * nt;
     double* fp = smx;                       // [PCH]  w_p t_e / den_p
-    double* spre = smx + PCH;               // [PCH][S4]
+    double* spre = smx + ((PCH + 1) & ~1);  // [PCH][S4], 16-byte aligned for the double2 reads
     double* spost = spre + (size_t)PCH * S4;
     const int tid = threadIdx.x, p0 = blockIdx.x * PCH, np = min(PCH, P - p0);
     double* mine = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * S * S;
@@ -1231,7 +1476,7 @@ cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, 
                                                in->Ppad, scratch);
     } else {
         const int S4 = (in->S + 3) & ~3;
-        const size_t smem = sizeof(double) * ((size_t)pch + 2 * (size_t)pch * S4);
+        const size_t smem = sizeof(double) * ((size_t)((pch + 1) & ~1) + 2 * (size_t)pch * S4);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k_cross_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
