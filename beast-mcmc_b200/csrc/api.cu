@@ -508,6 +508,17 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             d.pBegin = pBegin; d.pEnd = pEnd;
             d.slots = (unsigned)(srcSlot1 & 0xFF) | ((unsigned)(srcSlot2 & 0xFF) << 8) | ((unsigned)(dstSlot & 0xFF) << 16);
             d.pad_ = o.kind;
+            d.pfA = d.pfB = 0; d.pfM1 = d.pfM2 = -1;
+            // register forwarding: inside one subtree walk a thread re-reads, as a child, exactly the cell it wrote for
+            // the previous op -- flag it (bit 1), with that child moved to position 1 (the product commutes exactly)
+            if (in->forward && !preOrder && !(maxDepth > 0 && subStack[subOfPos[pos]]) &&
+                pos > plan.subs[subOfPos[pos]].begin) {
+                const Op4& pv = ops4[pos - 1];
+                if (pv.pBegin == d.pBegin && pv.pEnd == d.pEnd) {
+                    if (!t1 && d.c1 == pv.dest) d.pad_ |= 2;
+                    else if (!t2 && d.c2 == pv.dest) { std::swap(d.c1, d.c2); std::swap(d.m1, d.m2); d.pad_ |= 2; }
+                }
+            }
         } else {
             DevOp& d = dops[pos];
             memset(&d, 0, sizeof d);
@@ -524,6 +535,33 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             d.pBegin = pBegin; d.pEnd = pEnd;
             d.srcSlot1 = d.srcSlot2 = d.dstSlot = -1;
             d.pad_ = o.kind;
+        }
+    }
+    if (fourPath && in->lookahead && !preOrder) {
+        // look-ahead fields: what op k+1 of the same walk will read from memory, except op k's own destination
+        // only where the phase is throughput-bound; a thin phase is a pure latency chain and the extra instructions cost
+        // more than the prefetch gives (measured on the 62-taxon benchmark2 alignment: +17 % with, in thin phases)
+        std::vector<char> thick(plan.subs.size(), 0);
+        const long perSub = (maxWindow + (32 / in->matCP) * in->walkR - 1) / ((32 / in->matCP) * in->walkR);
+        for (int ph = 0; ph < nPhases; ++ph) {
+            const bool t = (long)(plan.phaseStart[ph + 1] - plan.phaseStart[ph]) * perSub >= (long)in->smCount * 8;
+            for (int q = plan.phaseStart[ph]; q < plan.phaseStart[ph + 1]; ++q) thick[q] = t;
+        }
+        for (size_t sIdx = 0; sIdx < plan.subs.size(); ++sIdx) {
+            if ((maxDepth > 0 && subStack[sIdx]) || (!thick[sIdx] && in->lookahead < 2)) continue;
+            for (int pos = plan.subs[sIdx].begin; pos + 1 < plan.subs[sIdx].end; ++pos) {
+                Op4& d = ops4[pos];
+                const Op4& nx = ops4[pos + 1];
+                auto enc = [&](int child, bool fromRegisters) -> int {
+                    if (fromRegisters) return 0;
+                    if (child < 0) return ((-child - 1) << 1) | 1;
+                    return child == d.dest ? 0 : ((child + 1) << 1);
+                };
+                d.pfA = enc(nx.c1, (nx.pad_ & 2) != 0);
+                d.pfB = enc(nx.c2, false);
+                if (d.pfA == 0) { d.pfA = d.pfB; d.pfB = 0; }
+                d.pfM1 = nx.m1; d.pfM2 = nx.m2;
+            }
         }
     }
     const void* hostOps = fourPath ? (const void*)ops4.data() : (const void*)dops.data();
@@ -656,6 +694,8 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 0);
     in->reorder = envInt("B200_REORDER", 1);
+    in->forward = envInt("B200_FORWARD", 1);
+    in->lookahead = envInt("B200_LOOKAHEAD", 1);
     in->planCacheSize = std::max(0, std::min(16, envInt("B200_PLAN_CACHE", 4)));
     in->planCache.reserve(16);
     in->thinR1 = envInt("B200_THIN_R1", 1);

@@ -32,17 +32,22 @@ struct alignas(16) DevOp {
     int pad_;
 };
 
-// Compact operation record of the 4-state walk: 48 bytes = three warp-uniform 128-bit loads, all
+// Compact operation record of the 4-state walk: 64 bytes = four warp-uniform 128-bit loads, all
 // addressing by index so that no pointer has to be chased on the per-op critical path.
 //   dest/c1/c2 : partials slot (>= 0) in the contiguous slab, or -(tipIndex+1) for a compact tip
 //   m1/m2      : transition-matrix buffer index;  sw/sr/cum : scale buffer index or -1
 //   slots      : byte0 srcSlot1, byte1 srcSlot2, byte2 dstSlot of the shared-memory operand stack (0xFF = none)
+//   pad_       : bit 0 = pre-order op, bit 1 = child 1 is the previous op's result (taken from registers)
+//   pfA/pfB    : operands of the NEXT op of the walk that are already final in memory, prefetched into L1 while this
+//                op computes: 0 = none, ((slot + 1) << 1) = partials slot, (tip << 1) | 1 = compact tip states
+//   pfM1/pfM2  : the next op's matrix buffers (-1 = none)
 struct alignas(16) Op4 {
     int dest, c1, c2, m1;
     int m2, sw, sr, cum;
     int pBegin, pEnd;
     unsigned int slots;
     int pad_;
+    int pfA, pfB, pfM1, pfM2;
 };
 
 // one edge of a calculateEdgeDerivatives call
@@ -98,6 +103,8 @@ struct Instance {
     double* dBlockSums = nullptr;
     double* dOut = nullptr;                   // [maxPartitions + 1]
     unsigned int* dCounter = nullptr;
+    int lookahead = 1;                        // L1 prefetch of the next op's operands (B200_LOOKAHEAD)
+    int forward = 1;                          // register forwarding between consecutive ops of a walk (B200_FORWARD)
     double* dScratch = nullptr;               // grow-only workspace of the derivative calls
     size_t scratchDoubles = 0;
     int partitionCount = 1;

@@ -236,12 +236,17 @@ struct WalkArgs {
 
 __device__ __forceinline__ Op4 loadOp(const Op4* p) {
     const int4* q = reinterpret_cast<const int4*>(p);
-    int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
     Op4 o;
     o.dest = a.x; o.c1 = a.y; o.c2 = a.z; o.m1 = a.w;
     o.m2 = b.x; o.sw = b.y; o.sr = b.z; o.cum = b.w;
     o.pBegin = c.x; o.pEnd = c.y; o.slots = (unsigned)c.z; o.pad_ = c.w;
+    o.pfA = d.x; o.pfB = d.y; o.pfM1 = d.z; o.pfM2 = d.w;
     return o;
+}
+
+__device__ __forceinline__ void prefetchL1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
 }
 
 // non-volatile: a read-only load the scheduler may hoist freely
@@ -335,12 +340,55 @@ k_walk4(const WalkArgs A) {
     const int last = range.y - 1;
 
     Op4 cur = loadOp(A.ops + range.x);
+    double d[R][4];                                            // survives the loop: op k+1 may take it as its first child
+#pragma unroll
+    for (int r = 0; r < R; ++r) d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.0;
     for (int k = range.x; k <= last; ++k) {
-        const Op4 nxt = loadOp(A.ops + min(k + 1, last));      // one record ahead, off the dependent chain
+        // records: k+2 starts its trip to L1 now; k+1 is read (an L1 hit by then) only after this op's arithmetic, so
+        // that its 16 registers are not live across the register-hungry part of the body
+        // (R = 1, the latency-chain configuration, has registers to spare and reads k+1 a whole op ahead instead)
+        Op4 nxt;
+        if (R == 1) nxt = loadOp(A.ops + min(k + 1, last));
+        else if (lane == 0) prefetchL1(A.ops + min(k + 2, last));
         const int s1 = cur.slots & 0xFF, s2 = (cur.slots >> 8) & 0xFF, sd = (cur.slots >> 16) & 0xFF;
-        double d[R][4];
+        if (!PRE && !STACK) {
+            // look-ahead: the NEXT op's memory operands (never this op's destination) start their trip to L1 now,
+            // so that its loads find them there when this op is done
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int pf = w == 0 ? cur.pfA : cur.pfB;
+                if (pf == 0) continue;
+                if (pf & 1) {
+                    const uint8_t* t = A.states + (size_t)(pf >> 1) * A.Ppad + p0;
+                    if ((lane % G) == 0 && c == 0) prefetchL1(t);          // G*R consecutive bytes: one line
+                } else if (catValid) {
+                    const double* xg = A.partials + (size_t)((pf >> 1) - 1) * A.stride + off0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (p0 + r * G < A.Ppad) prefetchL1(xg + (size_t)r * G * 4);
+                }
+            }
+            if (lane < 8) {
+                const int mi = lane < 4 ? cur.pfM1 : cur.pfM2;
+                if (mi >= 0) prefetchL1(A.mats + (size_t)mi * A.matStride + (lane & 3) * 4 * CP);
+            }
+        }
         if (!PRE) {
-            childTerm<CP, R, STACK, true>(A, cur.c1, cur.m1, s1, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
+            if (!STACK && (cur.pad_ & 2)) {
+                // the first child is what this very thread produced for the previous op of the walk: take it from
+                // registers (no store -> L2 -> load round trip, one partial less through the LSU)
+                Mat4 M;
+                loadMat<CP>(A.mats + (size_t)cur.m1 * A.matStride + moff, M);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double v[4];
+                    applyMat(M, d[r], v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[r][i] = v[i];
+                }
+            } else {
+                childTerm<CP, R, STACK, true>(A, cur.c1, cur.m1, s1, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
+            }
             childTerm<CP, R, STACK, false>(A, cur.c2, cur.m2, s2, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
         } else {
             // pre-order op: q = pre[parent] (*) (M_sib post[sib]) at the parent, then down the node's own branch
@@ -361,6 +409,7 @@ k_walk4(const WalkArgs A) {
                 for (int j = 0; j < 4; ++j) d[r][j] = M1.r[j][0] * q[0] + M1.r[j][1] * q[1] + M1.r[j][2] * q[2] + M1.r[j][3] * q[3];
             }
         }
+        if (R != 1) nxt = loadOp(A.ops + min(k + 1, last));
         double* dg = A.partials + (size_t)cur.dest * A.stride + off0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -423,6 +472,7 @@ static cudaError_t launchWalk4R(Instance* in, const Op4* dOps, const int4* dSubs
     if (stackDepth > 0) return launchWalk4K<CP, R, true, 4>(in, A, grid, (size_t)stackDepth * 32 * R * 128);
     if (in->walkMinBlocks >= 6) return launchWalk4K<CP, R, false, 6>(in, A, grid, 0);
     if (in->walkMinBlocks == 5) return launchWalk4K<CP, R, false, 5>(in, A, grid, 0);
+    if (in->walkMinBlocks == 3) return launchWalk4K<CP, R, false, 3>(in, A, grid, 0);
     return launchWalk4K<CP, R, false, 4>(in, A, grid, 0);
 }
 
