@@ -63,8 +63,10 @@ struct TimedScope {
     Instance* in;
     int cls;
     cudaEvent_t a = nullptr, b = nullptr;
-    TimedScope(Instance* i, int c) : in(i), cls(c) {
+    // `kernels`: how many kernel launches the bracket covers (a graph replay covers a whole plan)
+    TimedScope(Instance* i, int c, int kernels = 1) : in(i), cls(c) {
         if (in->timing) {
+            in->timedLaunches[cls] += kernels - 1;
             cudaEventCreate(&a);
             cudaEventCreate(&b);
             cudaEventRecord(a, in->stream);
@@ -127,7 +129,7 @@ void destroyInstance(Instance* in) {
     cudaSetDevice(in->device);
     if (in->stream) cudaStreamSynchronize(in->stream);
     cudaFree(in->partialsBase); cudaFree(in->states8Base); cudaFree(in->states32Base);
-    for (CachedPlan& cp : in->planCache) cudaFree(cp.dBlock);
+    for (CachedPlan& cp : in->planCache) { if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec); cudaFree(cp.dBlock); }
     cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dRates); cudaFree(in->dWeights);
     cudaFree(in->dFreqs); cudaFree(in->dScale); cudaFree(in->dPatternWeights);
     cudaFree(in->dPatternPartitions); cudaFree(in->dSite); cudaFree(in->dBlockSums); cudaFree(in->dOut);
@@ -329,6 +331,30 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
                 memcmp(cp.key.data(), hops.data(), sizeof(HostOp) * (size_t)n) != 0)
                 continue;
             cp.lastUse = ++in->planClock;
+            cp.hits++;
+            // A plan that keeps coming back and needs several dependent launches is replayed as ONE graph launch:
+            // on small alignments the host-side launch cost, not the kernels, sets the pace.
+            int launches = 0;
+            for (size_t ph = 0; ph + 1 < cp.phaseStart.size(); ++ph) launches += cp.phaseStart[ph + 1] > cp.phaseStart[ph];
+            if (in->useGraphs && launches >= 2) {
+                if (cp.graphExec == nullptr && cp.hits >= 2 && !in->timing &&
+                    cudaStreamBeginCapture(in->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const cudaError_t e1 = launchPlan(in, cp.dBlock, static_cast<char*>(cp.dBlock) + cp.subsOffset, cp.phaseStart,
+                                                      cp.phaseDepth, cp.fourPath, cp.maxWindow, cp.preOrder);
+                    cudaGraph_t g = nullptr;
+                    const cudaError_t e2 = cudaStreamEndCapture(in->stream, &g);
+                    if (e1 != cudaSuccess || e2 != cudaSuccess || g == nullptr ||
+                        cudaGraphInstantiate(&cp.graphExec, g, 0) != cudaSuccess)
+                        cp.graphExec = nullptr;
+                    if (g) cudaGraphDestroy(g);
+                    cudaGetLastError();
+                }
+                if (cp.graphExec != nullptr) {
+                    TimedScope ts(in, T_PARTIALS, launches);
+                    CUDA_OK(cudaGraphLaunch(cp.graphExec, in->stream));
+                    return BEAGLE_SUCCESS;
+                }
+            }
             CUDA_OK(launchPlan(in, cp.dBlock, static_cast<char*>(cp.dBlock) + cp.subsOffset, cp.phaseStart, cp.phaseDepth,
                                cp.fourPath, cp.maxWindow, cp.preOrder));
             return BEAGLE_SUCCESS;
@@ -589,6 +615,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         for (CachedPlan& cp : in->planCache) if (cp.dBlock == nullptr || cp.lastUse < slot->lastUse) slot = &cp;
         const size_t subsOffset = (opBytes + 255) & ~size_t(255);
         const size_t need = subsOffset + subBytes;
+        if (slot->graphExec) { cudaGraphExecDestroy(slot->graphExec); slot->graphExec = nullptr; }
+        slot->hits = 0;
         if (slot->capacity < need) {
             if (slot->dBlock) cudaFree(slot->dBlock);
             slot->dBlock = nullptr; slot->capacity = 0;
@@ -685,7 +713,9 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
         in->matStride = (in->matStride + 3) & ~size_t(3);        // keep every buffer 32-byte aligned
     } else {
         in->matCP = 0;
-        in->matStride = 2 * (size_t)in->C * in->Sp * in->Sp;     // MT[c][j][i] then M[c][i][j] (tensor-path B operand)
+        // MT[c][j][i] (FMA walk, tip gathers), then the tensor-path operands with an (Sp+4)-double row stride so that ONE
+        // contiguous bulk copy lands them in shared memory bank-conflict free: M[c][i][.] and MT[c][j][.]
+        in->matStride = (size_t)in->C * in->Sp * (in->Sp + 2 * (size_t)(in->Sp + 4));
     }
     in->slotOf.assign(in->nBuffers, -1);
     in->partials.assign(in->nBuffers, nullptr);
@@ -696,6 +726,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->reorder = envInt("B200_REORDER", 1);
     in->forward = envInt("B200_FORWARD", 1);
     in->lookahead = envInt("B200_LOOKAHEAD", 1);
+    in->useGraphs = envInt("B200_GRAPHS", 1);
     in->planCacheSize = std::max(0, std::min(16, envInt("B200_PLAN_CACHE", 4)));
     in->planCache.reserve(16);
     in->thinR1 = envInt("B200_THIN_R1", 1);
@@ -1051,7 +1082,9 @@ int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMat
                         else mt[(size_t)c * 20 + 16 + q] = 1.0;
                     }
                 } else {
-                    t[(size_t)in->C * in->Sp * in->Sp + ((size_t)c * in->Sp + i) * in->Sp + j] = v;
+                    const size_t ld = (size_t)in->Sp + 4, half = (size_t)in->C * in->Sp * in->Sp;
+                    t[half + ((size_t)c * in->Sp + i) * ld + j] = v;
+                    t[half + (size_t)in->C * in->Sp * ld + ((size_t)c * in->Sp + j) * ld + i] = v;
                 }
             }
     CUDA_OK(cudaMemcpyAsync(in->dMat + matrixIndex * n, t.data(), sizeof(double) * n, cudaMemcpyHostToDevice, in->stream));

@@ -65,6 +65,8 @@ struct CachedPlan {
     std::vector<int> phaseStart, phaseDepth;
     int maxWindow = 0;
     long lastUse = 0;
+    long hits = 0;
+    cudaGraphExec_t graphExec = nullptr;      // the plan's phase launches as one graph launch (plans with >= 2 launches)
 };
 
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
@@ -103,6 +105,7 @@ struct Instance {
     double* dBlockSums = nullptr;
     double* dOut = nullptr;                   // [maxPartitions + 1]
     unsigned int* dCounter = nullptr;
+    int useGraphs = 1;                        // B200_GRAPHS
     int lookahead = 1;                        // L1 prefetch of the next op's operands (B200_LOOKAHEAD)
     int forward = 1;                          // register forwarding between consecutive ops of a walk (B200_FORWARD)
     double* dScratch = nullptr;               // grow-only workspace of the derivative calls

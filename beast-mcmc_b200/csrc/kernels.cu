@@ -99,7 +99,10 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
         out[(size_t)j * rowStride + i] = acc;
         if (!matCP) {
             // generic layout: second half of the buffer holds the row-major M[c][i][j] (tensor-path B operand)
-            matBase[(size_t)probIdx[b] * matStride + (size_t)C * Sp * Sp + ((size_t)c * Sp + i) * Sp + j] = acc;
+            const size_t ld = (size_t)Sp + 4;
+            double* padded = matBase + (size_t)probIdx[b] * matStride + (size_t)C * Sp * Sp;
+            padded[((size_t)c * Sp + i) * ld + j] = acc;                                   // M[c][i][.]
+            padded[(size_t)C * Sp * ld + ((size_t)c * Sp + j) * ld + i] = acc;             // MT[c][j][.]
         } else {
             // tensor-path copies after the [j][CP][i] block (k_walk4t):
             //   Mpad[c][8][4] : B fragment, lane (g,t) reads [g][t]; rows g >= 4 stay zero
@@ -146,7 +149,8 @@ k_transition_mma(const double* __restrict__ eigenBase, size_t eigenStride, int S
     __syncthreads();
     const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     double* outT = matBase + (size_t)probIdx[b] * matStride + (size_t)c * Sp * Sp;                     // MT[j][i]
-    double* outR = matBase + (size_t)probIdx[b] * matStride + (size_t)C * Sp * Sp + (size_t)c * Sp * Sp;  // M[i][j]
+    double* outR = matBase + (size_t)probIdx[b] * matStride + (size_t)C * Sp * Sp + (size_t)c * Sp * LD;  // M[i][.], stride LD
+    double* outTp = outR + (size_t)C * Sp * LD;                                                            // MT[j][.], stride LD
     for (int mt = w; mt < NT; mt += 4) {             // 8-row tiles of the output
         double acc[NT][2];
 #pragma unroll
@@ -164,9 +168,11 @@ k_transition_mma(const double* __restrict__ eigenBase, size_t eigenStride, int S
         for (int n = 0; n < NT; ++n) {
             const int j = 8 * n + 2 * t;
             const double v0 = fabs(acc[n][0]), v1 = fabs(acc[n][1]);
-            *reinterpret_cast<double2*>(outR + (size_t)i * Sp + j) = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(outR + (size_t)i * LD + j) = make_double2(v0, v1);
             outT[(size_t)j * Sp + i] = v0;
             outT[(size_t)(j + 1) * Sp + i] = v1;
+            outTp[(size_t)j * LD + i] = v0;
+            outTp[(size_t)(j + 1) * LD + i] = v1;
         }
     }
 }
@@ -682,10 +688,11 @@ k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int
             __syncthreads();
             const bool pre = op.pad_ == 1;
             // pre-order ops use the ROW-MAJOR copy of the node's own matrix (second half of the buffer)
-            const double* m1g = op.m1 + (pre ? (size_t)C * Sp * Sp : 0) + (size_t)c * Sp * Sp;
+            const int ld1 = pre ? Sp + 4 : Sp;       // the row-major copy carries the tensor path's padded row stride
+            const double* m1g = op.m1 + (pre ? (size_t)C * Sp * Sp + (size_t)c * Sp * ld1 : (size_t)c * Sp * Sp);
             const double* m2g = op.m2 + (size_t)c * Sp * Sp;
             if (stageMatrices) {
-                for (int q = tid; q < Sp * Sp; q += nt) { mt1s[q] = m1g[q]; mt2s[q] = m2g[q]; }
+                for (int q = tid; q < Sp * Sp; q += nt) { mt1s[q] = m1g[(q / Sp) * ld1 + (q % Sp)]; mt2s[q] = m2g[q]; }
             }
             const size_t tileOff = ((size_t)c * Ppad + p0) * Sp;
             if (op.c1) for (int q = tid; q < tileElems; q += nt) x1[q] = op.c1[tileOff + q];
@@ -719,7 +726,7 @@ k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int
                     if (!(p >= op.pBegin && p < op.pEnd && p < range.w)) continue;
                     double d = 0.0;
                     const double* qr = qt + (size_t)pl * Sp;
-                    for (int i = 0; i < S; ++i) d += qr[i] * mt1[(size_t)i * Sp + j];
+                    for (int i = 0; i < S; ++i) d += qr[i] * mt1[(size_t)i * (stageMatrices ? Sp : ld1) + j];
                     op.dest[tileOff + q] = d;
                     if (doMax) atomicMax(&pmax[pl], (unsigned long long)__double_as_longlong(d));
                 }
@@ -801,60 +808,79 @@ __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmemSrc) : "memory");
 }
 
-// Block = WARPS warps x 16 patterns.  The two matrices of the NEXT (op, category) pair are fetched with
-// cp.async (LDGSTS) into the other half of a double buffer while the tensor pipe works on the current pair.
-template <int NT, int WARPS, bool DB, bool PRE>
-__global__ void __launch_bounds__(WARPS * 32)
+// ---- TMA (1-D bulk copy) staging: one elected thread moves a whole padded matrix, completion on an mbarrier ----
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulkCopyG2S(void* smemDst, const void* gmemSrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc), "r"(bytes),
+                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// Block = WARPS warps x 16 patterns.  Per (op, category) ONE thread issues two bulk copies (TMA engine, SASS UBLKCP):
+// the matrices sit in global memory already in the padded [Sp][Sp+4] shape the fragment loads want, so each is one
+// contiguous transfer; everyone else waits on the mbarrier and spends no issue slots on staging.  Single buffer: the
+// other resident blocks of the SM cover the copy (measured faster than a double buffer at one block per SM).
+template <int NT, int WARPS, bool PRE>
+__global__ void __launch_bounds__(WARPS * 32, 3)
 k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int C, int Ppad, int logScalers) {
     constexpr int Sp = 8 * NT;
     constexpr int LD = Sp + 4;                       // shared-memory row stride (doubles)
-    constexpr int NTHREADS = WARPS * 32;
     constexpr int MATSZ = Sp * LD;
-    extern __shared__ double smm[];                  // [2 buffers][2 matrices][Sp][LD]
+    constexpr unsigned MATBYTES = MATSZ * sizeof(double);
+    extern __shared__ __align__(128) double smw[];   // [2 matrices][Sp][LD]
+    __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int4 range = subs[blockIdx.y];
     if (range.z + blockIdx.x * (WARPS * 16) >= range.w) return;      // block outside this subtree's pattern window
     const int pw = range.z + blockIdx.x * (WARPS * 16) + w * 16;      // first pattern of this warp's 16-row tile
-    const size_t mRow = (size_t)C * Sp * Sp;         // offset of the row-major copies in a matrix buffer
+    const size_t mRow = (size_t)C * Sp * Sp;         // offset of the padded row-major copies in a matrix buffer
+    const size_t mTp = mRow + (size_t)C * MATSZ;     // offset of the padded transposed copies
     const int total = (range.y - range.x) * C;
-
-    auto stageAsync = [&](int flat, int buf) {
-        const DevOp* o = ops + range.x + flat / C;
-        const int c = flat % C;
-        // pre-order ops contract over the ROW index of the node's own matrix: stage its transposed copy (first half)
-        const double* g1 = o->m1 + (PRE ? 0 : mRow) + (size_t)c * Sp * Sp;
-        const double* g2 = o->m2 + mRow + (size_t)c * Sp * Sp;
-        double* s1 = smm + (size_t)buf * 2 * MATSZ;
-        double* s2 = s1 + MATSZ;
-        for (int q = tid; q < Sp * Sp / 2; q += NTHREADS) {
-            const int i = (2 * q) / Sp, j = (2 * q) % Sp;
-            cpAsync16(s1 + i * LD + j, g1 + 2 * q);
-            cpAsync16(s2 + i * LD + j, g2 + 2 * q);
-        }
-    };
-
-    if (DB) {
-        stageAsync(0, 0);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid == 0) {
+        mbarInit(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    unsigned parity = 0;
+
     bool act[2] = {false, false};
     double rowMax[2] = {0.0, 0.0};
     for (int flat = 0; flat < total; ++flat) {
-        if (DB) {
-            if (flat + 1 < total) stageAsync(flat + 1, (flat + 1) & 1);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            // single buffer: more resident blocks per SM hide the staging instead (measured faster at Sp = 64)
-            stageAsync(flat, 0);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (tid == 0) {
+            const DevOp* o = ops + range.x + flat / C;
+            const int cs = flat % C;
+            // pre-order ops contract over the ROW index of the node's own matrix: stage its transposed copy
+            const double* g1 = o->m1 + (PRE ? mTp : mRow) + (size_t)cs * MATSZ;
+            const double* g2 = o->m2 + mRow + (size_t)cs * MATSZ;
+            // the generic-proxy reads of the previous pair (ordered by the barrier that ended it) precede these writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbarExpectTx(&bar, 2 * MATBYTES);
+            bulkCopyG2S(smw, g1, MATBYTES, &bar);
+            bulkCopyG2S(smw + MATSZ, g2, MATBYTES, &bar);
         }
-        __syncthreads();
+        mbarWait(&bar, parity);
+        parity ^= 1;
         const DevOp op = ops[range.x + flat / C];
         const int c = flat % C;
-        const double* P1 = smm + (size_t)(DB ? (flat & 1) : 0) * 2 * MATSZ;
+        const double* P1 = smw;
         const double* P2 = P1 + MATSZ;
         if (c == 0) {
 #pragma unroll
@@ -1037,17 +1063,17 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
     }
 }
 
-template <int NT, int WARPS, bool PRE = false, bool DB = false>
+template <int NT, int WARPS, bool PRE = false>
 static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     constexpr int Sp = 8 * NT;
-    const size_t smem = (DB ? 4 : 2) * (size_t)Sp * (Sp + 4) * sizeof(double);
+    const size_t smem = 2 * (size_t)Sp * (Sp + 4) * sizeof(double);
     if (smem > in->mmaSmemConfigured[PRE ? 1 : 0]) {
-        cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, DB, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         in->mmaSmemConfigured[PRE ? 1 : 0] = smem;
     }
     dim3 grid((maxWindow + WARPS * 16 - 1) / (WARPS * 16), nSubs);
-    k_walk_mma<NT, WARPS, DB, PRE><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
+    k_walk_mma<NT, WARPS, PRE><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -1068,7 +1094,7 @@ cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs
             case 2: return launchWalkMmaT<2, 4>(in, dOps, dSubs, nSubs, maxWindow);
             case 3: return launchWalkMmaT<3, 4>(in, dOps, dSubs, nSubs, maxWindow);
             case 4: return launchWalkMmaT<4, 4>(in, dOps, dSubs, nSubs, maxWindow);
-            case 8: return in->mmaWarps == 8 ? launchWalkMmaT<8, 8, false, true>(in, dOps, dSubs, nSubs, maxWindow) : launchWalkMmaT<8, 4>(in, dOps, dSubs, nSubs, maxWindow);
+            case 8: return launchWalkMmaT<8, 4>(in, dOps, dSubs, nSubs, maxWindow);
             default: break;      // other state counts: FMA block walk below
         }
     }
@@ -1185,11 +1211,8 @@ k_edge_derivatives_mma(const EdgeRef* __restrict__ edges, const double* __restri
     }
     for (int c = 0; c < C; ++c) {
         __syncthreads();                             // everyone is done with the previous category's matrix
-        const double* gD = e.D + mRow + (size_t)c * Sp * Sp;
-        for (int q = tid; q < Sp * Sp / 2; q += 128) {
-            const int i = (2 * q) / Sp, j = (2 * q) % Sp;
-            cpAsync16(smm + i * LD + j, gD + 2 * q);
-        }
+        const double* gD = e.D + mRow + (size_t)c * Sp * LD;      // padded row-major copy: already in the shared-memory shape
+        for (int q = tid; q < Sp * LD / 2; q += 128) cpAsync16(smm + 2 * q, gD + 2 * q);
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();

@@ -42,8 +42,12 @@ from beast_mcmc_b200 import treedatalikelihood as tdl  # noqa: E402
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1
     "gtr_g4_1000x10k": dict(taxa=1000, patterns=10000, states=4, categories=4, rootHeight=0.1, treeSeed=20240924),
+    # the same with a scale buffer written by every op ("also run with scaleWrite on every op")
+    "gtr_g4_1000x10k_rescaled": dict(taxa=1000, patterns=10000, states=4, categories=4, rootHeight=0.1, treeSeed=20240924,
+                                     scaling=True, data="gtr_g4_1000x10k"),
     # configs[2]: codon model on the dense-contraction path
     "codon_mg94_500x5k": dict(taxa=500, patterns=5000, states=61, categories=1, rootHeight=0.1, treeSeed=2),
+    "codon_mg94_500x5k_g4": dict(taxa=500, patterns=5000, states=61, categories=4, rootHeight=0.1, treeSeed=2),
     # configs[0]-like latency case (benchmark1.xml shape: 1441 taxa, 593 patterns, HKY, no gamma)
     "hky_1441x593": dict(taxa=1441, patterns=593, states=4, categories=1, rootHeight=0.1, treeSeed=1441),
     # configs[0] as shipped: the reference's own benchmark alignments (tests/golden/benchmark{1,2}_patterns.npz, extracted
@@ -83,7 +87,7 @@ def build_workload(name, shard_index, overrides):
         else em.GammaSiteRateModel()
     # the simulated alignment is cached per box (sweeps re-use it); it is regenerated when absent
     cache = os.path.join(os.environ.get("B200_BENCH_CACHE", "/tmp/b200_bench_cache"),
-                         f"{name}_{w['taxa']}_{w['patterns']}_{w['states']}_{w['categories']}_{shard_index}.npz")
+                         f"{w.get('data', name)}_{w['taxa']}_{w['patterns']}_{w['states']}_{w['categories']}_{shard_index}.npz")
     if w.get("fixture"):
         z = np.load(os.path.join(ROOT, "tests", "golden", w["fixture"] + "_patterns.npz"))
         pats = em.Patterns(z["states"].astype(np.int32), z["weights"], 4)
@@ -448,10 +452,16 @@ def main():
         step_e2e(k)
     bracket()
     t0 = time.perf_counter()
+    per_call = []
     for k in range(args.steps):
+        tc = time.perf_counter()
         last = step_e2e(k)
+        per_call.append(time.perf_counter() - tc)
     bracket()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    per_call.sort()
+    e2e_dist = {q: 1e3 * per_call[min(len(per_call) - 1, int(f * len(per_call)))] for q, f in
+                (("p10_ms", 0.10), ("median_ms", 0.50), ("p90_ms", 0.90))}
     clocks = sampler.stop() if sampler else None
 
     # ---- secondary: the incremental evaluation MCMC mostly issues (one tip-to-root path dirty) ------------
@@ -533,7 +543,8 @@ def main():
                      "other_kernels_ms_per_step": {"transition_matrices": m_ms / args.steps,
                                                    "root": r_ms / args.steps}},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "evals/s", "ms_per_step": 1e3 * e2e_s / args.steps,
-                "h2d_bytes_per_step": ev.h2d_bytes(S, C), "d2h_bytes_per_step": 8, "logL": float(last)},
+                "h2d_bytes_per_step": ev.h2d_bytes(S, C), "d2h_bytes_per_step": 8, "logL": float(last),
+                "per_call_rank0": e2e_dist},
         "gpu_launches": int(k_n + m_n + r_n),
         "clocks": clocks,
         "incremental": inc,
@@ -551,6 +562,8 @@ def main():
                                           f"oracle/beagle_cpu.c with {threads} pthreads (fastest of "
                                           f"{[t for t, _ in tried]})",
                                 "logL": cval, "rel_diff_vs_gpu": abs(cval - logL) / abs(cval)}
+        t1, _ = cpu_time_evaluations(evc, S, C, P, 1, 1, 0.0)
+        line["cpu_baseline"]["single_thread"] = 1.0 / statistics.median(t1)
         if inc is not None:
             from oracle import cpu
             cinst = create_instance(cpu.factory(threads=threads), evc, S, C, P, None)
