@@ -465,15 +465,17 @@ def test_plan_cache_hits_and_invalidation():
     import os
     tree, pats, model, site = H.synthetic_case(40, 300, 4, seed=77)
 
-    def run(cache):
+    def run(cache, graphs="1"):
         os.environ["B200_PLAN_CACHE"] = cache
+        os.environ["B200_GRAPHS"] = graphs
         try:
             d = _delegate(tree.copy(), pats, model, site, GPU, rescalingScheme=S_.NONE)
         finally:
             os.environ.pop("B200_PLAN_CACHE", None)
+            os.environ.pop("B200_GRAPHS", None)
         like = tdl.TreeDataLikelihood(d, d and tree)
         out = []
-        for _ in range(4):                                  # same list, alternating parities -> cache hits
+        for _ in range(10):                                 # same list, alternating parities -> cache hits, then graph replays
             like.makeDirty()
             out.append(like.getLogLikelihood())
         like.updateNodeAndChildren(tree.tipCount + 3)       # a different (short) list
@@ -489,6 +491,6 @@ def test_plan_cache_hits_and_invalidation():
         d.finalize()
         return out
 
-    a, b = run("4"), run("0")
-    assert a == b, (a, b)
-    assert a[0] == a[1] == a[2] == a[3] == a[6] and a[5] != a[0]
+    a, b, c = run("4"), run("0"), run("4", graphs="0")
+    assert a == b == c, (a, b, c)
+    assert len(set(a[:10])) == 1 and a[12] == a[0] and a[11] != a[0]

@@ -20,6 +20,12 @@ python bench.py --workload hky_1441x593 --steps 1000 --warmup 10 --cpu-budget 4 
 python bench.py --workload makona_like_1610x6k --steps 500 --warmup 10 --cpu-budget 6 2>&1 | tail -1 > gpurun_out/${R}_bench_makona_like.json
 python bench.py --workload benchmark1_xml --steps 1000 --warmup 10 --cpu-budget 4 2>&1 | tail -1 > gpurun_out/${R}_bench_benchmark1_xml.json
 python bench.py --workload benchmark2_xml --steps 1000 --warmup 10 --cpu-budget 4 2>&1 | tail -1 > gpurun_out/${R}_bench_benchmark2_xml.json
+python bench.py --workload gtr_g4_1000x10k_rescaled --steps 500 --warmup 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/${R}_bench_cfg2_rescaled.json
+python bench.py --workload codon_mg94_500x5k_g4 --steps 50 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/${R}_bench_codon_g4.json
+python tools/bench_gradient.py > /dev/null 2>&1
+WORKLOAD=codon_mg94_500x5k STEPS=5 python tools/bench_gradient.py > /dev/null 2>&1
+STEPS=100 python tools/bench_partitions.py 2>&1 | tail -1 > gpurun_out/${R}_bench_partitions.json
+bash tools/sanitize.sh > gpurun_out/${R}_sanitizer.txt 2>&1; cat gpurun_out/${R}_sanitizer.txt
 for f in gpurun_out/${R}_bench_*.json; do python - $f <<'PY'
 import json, sys
 try:
