@@ -431,9 +431,14 @@ k_walk4(const WalkArgs A) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) d[r][i] *= inv;
                 if (active && c == 0) {
-                    const double lm = log(m);
-                    A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
-                    if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
+                    // BEAST's protocol (raw scalers, accumulation in a separate call) needs no logarithm here
+                    if (A.logScalers || cur.cum >= 0) {
+                        const double lm = log(m);
+                        A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
+                        if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
+                    } else {
+                        A.scale[(size_t)cur.sw * A.Ppad + p] = m;
+                    }
                 }
                 __syncwarp();
             } else if (cur.sr >= 0) {
