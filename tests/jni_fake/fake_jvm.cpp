@@ -88,7 +88,7 @@ template <typename F> static F sym(void* h, const char* name) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { fprintf(stderr, "usage: fake_jvm <libhmsbeagle-jni.so> info|tiny [fixture]\n"); return 1; }
+    if (argc < 3) { fprintf(stderr, "usage: fake_jvm <libhmsbeagle-jni.so> info|tiny|gradient [fixture]\n"); return 1; }
     void* h = dlopen(argv[1], RTLD_NOW | RTLD_GLOBAL);
     if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 1; }
     static JNINativeInterface_ table;
@@ -131,7 +131,8 @@ int main(int argc, char** argv) {
     fclose(f);
     typedef jint (*create_t)(JNIEnv*, jobject, jint, jint, jint, jint, jint, jint, jint, jint, jint, jintArray, jint, jlong, jlong, jobject);
     jobject details = J(new FakeObj);
-    jint inst = sym<create_t>(h, "createInstance")(env, self, 3, 2, 3, 4, nPat, 1, 4, 1, 0, IA({1, 0}), 2, 0, 0, details);
+    // 2 post-order + 5 pre-order partials buffers (indices 3,4 and 5..9), 4 branch matrices + 1 differential matrix
+    jint inst = sym<create_t>(h, "createInstance")(env, self, 3, 7, 3, 4, nPat, 1, 5, 1, 0, IA({1, 0}), 2, 0, 0, details);
     if (inst < 0) { fprintf(stderr, "createInstance returned %d\n", inst); return 4; }
     printf("instance %d resource=%lld impl=%s flags=%lld\n", inst, O(details)->ifields["setResourceNumber"],
            O(details)->sfields["setImplementationName"].c_str(), O(details)->ifields["setFlags"]);
@@ -160,6 +161,30 @@ int main(int argc, char** argv) {
     sym<jint (*)(JNIEnv*, jobject, jint, jdoubleArray)>(h, "getSiteLogLikelihoods")(env, self, inst, site);
     double s = 0; for (double v : O(site)->dbls) s += v;
     printf("siteSum %.5f\n", s);
+    if (std::string(argv[2]) == "gradient") {
+        // the pre-order / derivative natives (AbstractBeagleGradientDelegate, SubstitutionModelCrossProductDelegate):
+        // pre-order buffer of node k = 5 + k, root = node 4
+        std::vector<jdouble> rootPre(4 * nPat, 0.25);
+        if (sym<jint (*)(JNIEnv*, jobject, jint, jint, jdoubleArray)>(h, "setPartials")(env, self, inst, 9, DA(rootPre))) return 8;
+        // [dest pre, sw, sr, parent pre, own matrix, sibling post, sibling matrix]
+        if (sym<jint (*)(JNIEnv*, jobject, jint, jintArray, jint, jint)>(h, "updatePrePartials")(
+                env, self, inst, IA({8, -1, -1, 9, 3, 2, 2,   7, -1, -1, 9, 2, 3, 3,   5, -1, -1, 8, 0, 1, 1,   6, -1, -1, 8, 1, 0, 0}), 4, -1)) return 8;
+        std::vector<jdouble> Q(16, 1.0 / 3.0);
+        for (int i = 0; i < 4; ++i) Q[5 * i] = -1.0;
+        if (sym<jint (*)(JNIEnv*, jobject, jint, jint, jdoubleArray)>(h, "setDifferentialMatrix")(env, self, inst, 4, DA(Q))) return 8;
+        jdoubleArray sum = DA(std::vector<jdouble>(4, 0.0)), sumSq = DA(std::vector<jdouble>(4, 0.0));
+        rc = sym<jint (*)(JNIEnv*, jobject, jint, jintArray, jintArray, jintArray, jintArray, jint, jdoubleArray, jdoubleArray, jdoubleArray)>(
+            h, "calculateEdgeDifferentials")(env, self, inst, IA({0, 1, 2, 3}), IA({5, 6, 7, 8}), IA({4, 4, 4, 4}), IA({0}), 4,
+                                             nullptr, sum, sumSq);
+        printf("edge rc %d %.9f %.9f %.9f %.9f\n", rc, O(sum)->dbls[0], O(sum)->dbls[1], O(sum)->dbls[2], O(sum)->dbls[3]);
+        jdoubleArray cross = DA(std::vector<jdouble>(16, 1.0));      // the call ADDS to what it is given
+        rc = sym<jint (*)(JNIEnv*, jobject, jint, jintArray, jintArray, jintArray, jintArray, jdoubleArray, jint, jdoubleArray, jdoubleArray)>(
+            h, "calculateCrossProductDifferentials")(env, self, inst, IA({0, 1, 2, 3}), IA({5, 6, 7, 8}), IA({0}), IA({0}),
+                                                     DA({0.1, 0.1, 0.2, 0.1}), 4, cross, nullptr);
+        printf("cross rc %d", rc);
+        for (double v : O(cross)->dbls) printf(" %.9f", v - 1.0);
+        printf("\n");
+    }
     sym<jint (*)(JNIEnv*, jobject, jint)>(h, "finalize")(env, self, inst);
     return 0;
 }

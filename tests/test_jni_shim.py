@@ -73,3 +73,44 @@ def test_fake_jvm_tiny_test(jni, tmp_path):
     out = subprocess.run([exe, lib, "tiny", str(fx)], capture_output=True, text=True, check=True).stdout
     assert f"logL {expected:.5f} rc 0" in out, out
     assert "impl=B200-CUDA-Double" in out
+
+
+@pytest.mark.gpu
+def test_fake_jvm_gradient_natives(jni, tmp_path):
+    """updatePrePartials / setDifferentialMatrix / calculateEdgeDifferentials / calculateCrossProductDifferentials through
+    the JNI entry points (null output array, in/out array) against the oracle driven with the same calls."""
+    import numpy as np
+    from oracle.felsenstein import OracleBeagle
+    lib, exe = jni
+    tree, pats, model, site, expected = H.tiny_case()
+    fx = tmp_path / "tiny.txt"
+    with open(fx, "w") as f:
+        f.write(f"3 {pats.patternCount}\n")
+        for t in range(3):
+            f.write(" ".join(str(int(s)) for s in pats.states[t]) + "\n")
+    out = subprocess.run([exe, lib, "gradient", str(fx)], capture_output=True, text=True, check=True).stdout
+    P = pats.patternCount
+    o = OracleBeagle(3, 7, 3, 4, P, 1, 5, 1, 0)
+    for t in range(3):
+        o.setTipStates(t, pats.states[t])
+    o.setPatternWeights(np.ones(P))
+    e = model.getEigenDecomposition()
+    o.setEigenDecomposition(0, e.Evec, e.Ievc, e.Eval)
+    o.setCategoryRates(np.ones(1)); o.setCategoryWeights(0, np.ones(1)); o.setStateFrequencies(0, np.full(4, 0.25))
+    I = lambda *v: np.asarray(v, dtype=np.int32)
+    lengths = np.array([0.1, 0.1, 0.2, 0.1])
+    o.updateTransitionMatrices(0, I(0, 1, 2, 3), None, None, lengths, 4)
+    o.updatePartials(I(3, -1, -1, 0, 0, 1, 1, 4, -1, -1, 2, 2, 3, 3), 2, -1)
+    o.setPartials(9, np.full(4 * P, 0.25))
+    o.updatePrePartials(I(8, -1, -1, 9, 3, 2, 2, 7, -1, -1, 9, 2, 3, 3, 5, -1, -1, 8, 0, 1, 1, 6, -1, -1, 8, 1, 0, 0), 4, -1)
+    Q = np.full((4, 4), 1.0 / 3.0); np.fill_diagonal(Q, -1.0)
+    o.setDifferentialMatrix(4, Q.reshape(-1))
+    s1, s2 = np.zeros(4), np.zeros(4)
+    o.calculateEdgeDifferentials(I(0, 1, 2, 3), I(5, 6, 7, 8), I(4, 4, 4, 4), I(0), 4, None, s1, s2)
+    cross = np.zeros(16)
+    o.calculateCrossProductDifferentials(I(0, 1, 2, 3), I(5, 6, 7, 8), I(0), I(0), lengths, 4, cross, None)
+    edge = re.search(r"edge rc 0 (.*)", out).group(1).split()
+    got_cross = re.search(r"cross rc 0 (.*)", out).group(1).split()
+    assert np.allclose([float(v) for v in edge], s1, rtol=1e-8, atol=1e-8), (edge, s1)
+    assert np.allclose([float(v) for v in got_cross], cross, rtol=1e-7, atol=2e-8), (got_cross, cross)
+    assert f"logL {expected:.5f} rc 0" in out
