@@ -1523,6 +1523,125 @@ k_cross_generic(const EdgeRef* __restrict__ edges, int count, const double* __re
     }
 }
 
+// Tensor-pipe form for Sp = 8 NT: out[i][j] += sum_p A[p][i] B[p][j] is a GEMM whose contraction index is the pattern.
+// Block = one 32-pattern tile x a group of edges, 4 warps; per (edge, category) the scaled pre tile (A) and the post tile
+// (B) are staged in shared memory with the (Sp+4) row stride, warp w owns output rows 8(w + 4 mi) .. +7 and all columns:
+// lane (g,t) feeds A[i = 8m+g][k = t] and B[k = t][j = 8n+g] of every 4-pattern chunk to one m8n8k4 DMMA.
+template <int NT>
+__global__ void __launch_bounds__(128, 4)
+k_cross_mma(const EdgeRef* __restrict__ edges, int count, const double* __restrict__ rates,
+            const double* __restrict__ weights, const double* __restrict__ patternWeights, int S, int C, int P,
+            int Ppad, double* __restrict__ scratch) {
+    constexpr int Sp = 8 * NT, LDs = Sp + 4, TP = 32, MT = (NT + 3) / 4;
+    extern __shared__ double smc[];
+    double* sA = smc;                        // [TP][LDs]  w_p t_e / den_p * w_c r_c * pre
+    double* sB = smc + TP * LDs;             // [TP][LDs]  post
+    double* fp = sB + TP * LDs;              // [TP]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int p0 = blockIdx.x * TP, np = min(TP, P - p0);
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { acc[mi][n][0] = 0.0; acc[mi][n][1] = 0.0; }
+    for (int e = blockIdx.y; e < count; e += gridDim.y) {
+        const EdgeRef r = edges[e];
+        {   // per-pattern factor: 8 lanes per pattern, fixed-order shuffle reduction (fp is free: the last MMA pass synced)
+            const int pp = tid >> 3, l8 = tid & 7;
+            for (int base = 0; base < TP; base += 16) {
+                const int q = base + pp;
+                double d = 0.0;
+                if (q < np) {
+                    const int p = p0 + q;
+                    const int s = r.states ? r.states[p] : -1;
+                    for (int c = 0; c < C; ++c) {
+                        const double* pre = r.pre + ((size_t)c * Ppad + p) * Sp;
+                        double dc = 0.0;
+                        if (r.post) {
+                            const double* post = r.post + ((size_t)c * Ppad + p) * Sp;
+                            for (int k = l8; k < S; k += 8) dc += pre[k] * post[k];
+                        } else if (s < S) {
+                            if (l8 == (s & 7)) dc = pre[s];
+                        } else {
+                            for (int k = l8; k < S; k += 8) dc += pre[k];
+                        }
+                        d += weights[c] * dc;
+                    }
+                }
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                if (l8 == 0) fp[q] = q < np ? patternWeights[p0 + q] * r.len / d : 0.0;
+            }
+        }
+        __syncthreads();
+        for (int c = 0; c < C; ++c) {
+            const double f = weights[c] * rates[c];
+            for (int q2 = tid; q2 < TP * Sp / 2; q2 += 128) {
+                const int pp = (2 * q2) / Sp, k = (2 * q2) % Sp;
+                double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+                if (pp < np) {
+                    const size_t off = ((size_t)c * Ppad + p0 + pp) * Sp + k;
+                    const double sc = fp[pp] * f;
+                    a = *reinterpret_cast<const double2*>(r.pre + off);
+                    a.x = k < S ? a.x * sc : 0.0;
+                    a.y = k + 1 < S ? a.y * sc : 0.0;
+                    if (r.post) {
+                        b = *reinterpret_cast<const double2*>(r.post + off);
+                        if (k >= S) b.x = 0.0;
+                        if (k + 1 >= S) b.y = 0.0;
+                    } else {
+                        const int s = r.states[p0 + pp];
+                        b.x = (k < S && (s >= S || s == k)) ? 1.0 : 0.0;
+                        b.y = (k + 1 < S && (s >= S || s == k + 1)) ? 1.0 : 0.0;
+                    }
+                }
+                *reinterpret_cast<double2*>(sA + pp * LDs + k) = a;
+                *reinterpret_cast<double2*>(sB + pp * LDs + k) = b;
+            }
+            __syncthreads();
+#pragma unroll 2
+            for (int kc = 0; kc < TP / 4; ++kc) {
+                const double* arow = sA + (4 * kc + t) * LDs + g;
+                const double* brow = sB + (4 * kc + t) * LDs + g;
+                double a[MT];
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi) a[mi] = (w + 4 * mi < NT) ? arow[8 * (w + 4 * mi)] : 0.0;
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const double b = brow[8 * n];
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi)
+                        if (w + 4 * mi < NT) dmma884acc(acc[mi][n][0], acc[mi][n][1], a[mi], b);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    double* mine = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * S * S;
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+        const int m = w + 4 * mi, i = 8 * m + g;
+        if (m >= NT || i >= S) continue;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const int j = 8 * n + 2 * t;
+            if (j < S) mine[(size_t)i * S + j] = acc[mi][n][0];
+            if (j + 1 < S) mine[(size_t)i * S + j + 1] = acc[mi][n][1];
+        }
+    }
+}
+
+template <int NT>
+static cudaError_t launchCrossMmaT(Instance* in, const EdgeRef* dEdges, int count, const double* rates,
+                                   const double* weights, double* scratch, dim3 grid) {
+    constexpr int Sp = 8 * NT;
+    const size_t smem = sizeof(double) * (2 * 32 * (size_t)(Sp + 4) + 32);
+    k_cross_mma<NT><<<grid, 128, smem, in->stream>>>(dEdges, count, rates, weights, in->dPatternWeights, in->S, in->C,
+                                                     in->P, in->Ppad, scratch);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256)
 k_cross_reduce(const double* __restrict__ scratch, int nBlocks, int n, double* __restrict__ out) {
     const int q = blockIdx.x * 256 + threadIdx.x;
@@ -1533,36 +1652,52 @@ k_cross_reduce(const double* __restrict__ scratch, int nBlocks, int n, double* _
 }
 
 // scratch must hold crossProductBlocks() * S * S + S * S doubles; the result lands in the last S * S.
-int crossProductBlocks(const Instance* in, int count) {
+static void crossGeometry(const Instance* in, int count, int& pch, int& chunks, int& groups, bool& mma) {
     const bool four = in->Sp == 4;
-    const int pch = four ? 256 : std::max(1, std::min(32, 2048 / in->S));
-    const int chunks = (in->P + pch - 1) / pch;
-    const int groups = std::max(1, std::min(count, (2 * in->smCount + chunks - 1) / chunks));
+    const int nt = in->Sp / 8;
+    mma = !four && in->genericMma && in->Sp % 8 == 0 && ((nt >= 1 && nt <= 4) || nt == 8);
+    pch = four ? 256 : (mma ? 32 : std::max(1, std::min(32, 2048 / in->S)));
+    chunks = (in->P + pch - 1) / pch;
+    // the tensor form is a chain of short dependent phases per edge: fill every SM with 4 resident blocks
+    groups = std::max(1, std::min(count, ((mma ? 4 : 2) * in->smCount + chunks - 1) / chunks));
+}
+
+int crossProductBlocks(const Instance* in, int count) {
+    int pch, chunks, groups; bool mma;
+    crossGeometry(in, count, pch, chunks, groups, mma);
     return chunks * groups;
 }
 
 cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, const double* rates,
                                 const double* weights, double* scratch) {
-    const bool four = in->Sp == 4;
-    const int pch = four ? 256 : std::max(1, std::min(32, 2048 / in->S));
-    const int chunks = (in->P + pch - 1) / pch;
-    const int groups = std::max(1, std::min(count, (2 * in->smCount + chunks - 1) / chunks));
+    int pch, chunks, groups; bool mma;
+    crossGeometry(in, count, pch, chunks, groups, mma);
     const int n = in->S * in->S;
     dim3 grid(chunks, groups);
-    if (four) {
+    cudaError_t e = cudaSuccess;
+    if (in->Sp == 4) {
         k_cross4<<<grid, 256, 0, in->stream>>>(dEdges, count, rates, weights, in->dPatternWeights, in->C, in->P,
                                                in->Ppad, scratch);
+        e = cudaGetLastError();
+    } else if (mma) {
+        switch (in->Sp / 8) {
+            case 1: e = launchCrossMmaT<1>(in, dEdges, count, rates, weights, scratch, grid); break;
+            case 2: e = launchCrossMmaT<2>(in, dEdges, count, rates, weights, scratch, grid); break;
+            case 3: e = launchCrossMmaT<3>(in, dEdges, count, rates, weights, scratch, grid); break;
+            case 4: e = launchCrossMmaT<4>(in, dEdges, count, rates, weights, scratch, grid); break;
+            default: e = launchCrossMmaT<8>(in, dEdges, count, rates, weights, scratch, grid); break;
+        }
     } else {
         const int S4 = (in->S + 3) & ~3;
         const size_t smem = sizeof(double) * ((size_t)((pch + 1) & ~1) + 2 * (size_t)pch * S4);
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k_cross_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(k_cross_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
         k_cross_generic<<<grid, 256, smem, in->stream>>>(dEdges, count, rates, weights, in->dPatternWeights, in->S,
                                                          in->Sp, in->C, in->P, in->Ppad, pch, scratch);
+        e = cudaGetLastError();
     }
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_cross_reduce<<<(n + 255) / 256, 256, 0, in->stream>>>(scratch, chunks * groups, n,
                                                             scratch + (size_t)chunks * groups * n);
