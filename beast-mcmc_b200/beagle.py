@@ -164,6 +164,7 @@ _SIGNATURES = {
     "beagleCalculateCrossProductDerivative": ([_I, _IP, _IP, _IP, _IP, _DP, _I, _DP, _DP], _I),
     "b200SetKernelTiming": ([_I, _I], _I),
     "b200GetKernelTiming": ([_I, _I, _DP, C.POINTER(C.c_long)], _I),
+    "b200CompressSitePatterns": ([_I, _I, _I, _IP, _DP, _IP, _IP, _DP, _IP], _I),
     "b200HostAlloc": ([_L], C.c_void_p),
     "b200HostFree": ([C.c_void_p], None),
     "b200DebugPlan": ([_I if False else _IP, _I, _I, _I, _I, _I, _I, _I, _IP, _IP, _IP, _IP], _I),
@@ -467,3 +468,23 @@ class BeagleFactory:
         return BeagleJNIImpl(tipCount, partialsBufferCount, compactBufferCount, stateCount, patternCount,
                              eigenBufferCount, matrixBufferCount, categoryCount, scaleBufferCount,
                              resourceList, preferenceFlags, requirementFlags)
+
+
+def compressSitePatterns(states, siteWeights=None, resource: int = 1):
+    """SitePatterns (UNIQUE_ONLY) on the GPU: ``states`` int [taxa][sites] -> (patterns [taxa][P], weights [P],
+    sitePatternIndices [sites]); see b200CompressSitePatterns in include/libhmsbeagle_b200.h."""
+    lib = load_library()
+    a = np.ascontiguousarray(states, dtype=np.int32)
+    taxa, sites = a.shape
+    idx = np.zeros(max(sites, 1), dtype=np.int32)
+    pats = np.zeros(max(taxa * sites, 1), dtype=np.int32)
+    w = np.zeros(max(sites, 1), dtype=np.float64)
+    n = C.c_int(0)
+    sw = None if siteWeights is None else np.ascontiguousarray(siteWeights, dtype=np.float64)
+    rc = lib.b200CompressSitePatterns(resource, taxa, sites, a.ctypes.data_as(_IP),
+                                      None if sw is None else sw.ctypes.data_as(_DP), idx.ctypes.data_as(_IP),
+                                      pats.ctypes.data_as(_IP), w.ctypes.data_as(_DP), C.byref(n))
+    if rc != 0:
+        raise BeagleException("compressSitePatterns", rc)
+    P = n.value
+    return pats[:taxa * P].reshape(taxa, P).copy(), w[:P].copy(), idx[:sites].copy()

@@ -43,7 +43,7 @@ def lib_path(name="libhmsbeagle.so"):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "kernels.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "kernels.cu", "patterns.cu")]
     deps = srcs + [os.path.join(CSRC, "engine.h"), os.path.join(ROOT, "include", "libhmsbeagle_b200.h")]
     out = lib_path()
     if force or _stale(out, deps):

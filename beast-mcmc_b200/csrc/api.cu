@@ -1518,6 +1518,26 @@ int b200GetKernelTiming(int instance, int which, double* outMilliseconds, long* 
     return BEAGLE_SUCCESS;
 }
 
+int b200CompressSitePatterns(int resourceNumber, int taxonCount, int siteCount, const int* inStates,
+                             const double* inSiteWeights, int* outSitePatternIndices, int* outPatterns,
+                             double* outWeights, int* outPatternCount) {
+    BeagleResourceList* rl = beagleGetResourceList();
+    if (rl == nullptr || resourceNumber < 1 || resourceNumber >= rl->length) return BEAGLE_ERROR_NO_RESOURCE;
+    if (taxonCount < 1 || taxonCount > 65535 || siteCount < 0 || outPatternCount == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (siteCount > 0 && (inStates == nullptr || outSitePatternIndices == nullptr || outPatterns == nullptr ||
+                          outWeights == nullptr))
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    const int rc = compressSitePatterns(resourceNumber - 1, taxonCount, siteCount, inStates, outSitePatternIndices,
+                                        outPatterns, outWeights, outPatternCount);
+    if (rc != 0) return rc;
+    if (inSiteWeights != nullptr) {
+        // weights[i] += weight in site order, the order SitePatterns.addPattern adds them (:361-365)
+        for (int p = 0; p < *outPatternCount; ++p) outWeights[p] = 0.0;
+        for (int s = 0; s < siteCount; ++s) outWeights[outSitePatternIndices[s]] += inSiteWeights[s];
+    }
+    return BEAGLE_SUCCESS;
+}
+
 void* b200HostAlloc(long bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -157,6 +157,9 @@ cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs
 size_t edgeDerivativeWorkspace(const Instance* in, int count);
 cudaError_t launchEdgeDerivatives(Instance* in, const EdgeRef* dEdges, int count, const double* weights, double* outPerPattern,
                                   double* outSum, double* outSumSq, double* partial);
+// patterns.cu: unique site patterns in first-occurrence order (0 or a negative BEAGLE error code)
+int compressSitePatterns(int device, int taxa, int sites, const int* hStates, int* hPatternOfSite, int* hPatterns,
+                         double* hWeights, int* hPatternCount);
 int crossProductBlocks(const Instance* in, int count);
 cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, const double* rates,
                                 const double* weights, double* scratch);

@@ -320,6 +320,16 @@ BEAGLE_DLLEXPORT int b200RootLogLikelihoodDevice(int instance, int bufferIndex, 
                                                  int stateFrequenciesIndex, int cumulativeScaleIndex,
                                                  void** outDevicePointer, void** outStream);
 
+/* The step before the path: SitePatterns.addPatterns with CompressionType.UNIQUE_ONLY
+ * (src/dr/evolution/alignment/SitePatterns.java:226-372) on the GPU.  inStates is [taxon][site] (the int state codes
+ * SiteList.getSitePattern yields, any values); results: outSitePatternIndices[site], outPatterns [taxon][*outPatternCount]
+ * (capacity taxonCount*siteCount ints), outWeights[pattern] = sum of site weights (inSiteWeights NULL = 1 per site; added
+ * in site order like the Java), patterns numbered by first occurrence.  Not part of upstream beagle.h: a caller-side
+ * change (SitePatterns) would be needed to use it from BEAST. */
+BEAGLE_DLLEXPORT int b200CompressSitePatterns(int resourceNumber, int taxonCount, int siteCount, const int* inStates,
+                                              const double* inSiteWeights, int* outSitePatternIndices, int* outPatterns,
+                                              double* outWeights, int* outPatternCount);
+
 /* Host-logic test hook (no CUDA): the engine's execution plan for a 7-int-per-op list.  outOrder[n] = execution
  * position -> caller index; outSubs = (begin,end) position pairs of the independent subtree walks, grouped by phase;
  * outPhaseStart = index of each phase's first subtree (phases+1 entries); outCounts = {subtrees, phases}.
