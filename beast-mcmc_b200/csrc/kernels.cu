@@ -1546,8 +1546,11 @@ k_cross_mma(const EdgeRef* __restrict__ edges, int count, const double* __restri
         for (int n = 0; n < NT; ++n) { acc[mi][n][0] = 0.0; acc[mi][n][1] = 0.0; }
     for (int e = blockIdx.y; e < count; e += gridDim.y) {
         const EdgeRef r = edges[e];
-        {   // per-pattern factor: 8 lanes per pattern, fixed-order shuffle reduction (fp is free: the last MMA pass synced)
+        {   // per-pattern factor: 8 lanes per pattern, fixed-order shuffle reduction (fp is free: the last MMA pass synced).
+            // Fully unrolled with predicated loads: all 2 NT loads of a lane are in flight together (a rolled loop
+            // serialised one L2 round trip per 8 states and made this pass the whole kernel's critical path).
             const int pp = tid >> 3, l8 = tid & 7;
+#pragma unroll
             for (int base = 0; base < TP; base += 16) {
                 const int q = base + pp;
                 double d = 0.0;
@@ -1556,15 +1559,17 @@ k_cross_mma(const EdgeRef* __restrict__ edges, int count, const double* __restri
                     const int s = r.states ? r.states[p] : -1;
                     for (int c = 0; c < C; ++c) {
                         const double* pre = r.pre + ((size_t)c * Ppad + p) * Sp;
-                        double dc = 0.0;
-                        if (r.post) {
-                            const double* post = r.post + ((size_t)c * Ppad + p) * Sp;
-                            for (int k = l8; k < S; k += 8) dc += pre[k] * post[k];
-                        } else if (s < S) {
-                            if (l8 == (s & 7)) dc = pre[s];
-                        } else {
-                            for (int k = l8; k < S; k += 8) dc += pre[k];
+                        const double* post = r.post ? r.post + ((size_t)c * Ppad + p) * Sp : nullptr;
+                        double x[NT], y[NT];
+#pragma unroll
+                        for (int u = 0; u < NT; ++u) {
+                            const int k = l8 + 8 * u;
+                            x[u] = k < S ? pre[k] : 0.0;
+                            y[u] = post ? post[k] : ((s >= S || s == k) ? 1.0 : 0.0);
                         }
+                        double dc = 0.0;
+#pragma unroll
+                        for (int u = 0; u < NT; ++u) dc += x[u] * y[u];
                         d += weights[c] * dc;
                     }
                 }
@@ -1659,7 +1664,9 @@ static void crossGeometry(const Instance* in, int count, int& pch, int& chunks, 
     pch = four ? 256 : (mma ? 32 : std::max(1, std::min(32, 2048 / in->S)));
     chunks = (in->P + pch - 1) / pch;
     // the tensor form is a chain of short dependent phases per edge: fill every SM with 4 resident blocks
-    groups = std::max(1, std::min(count, ((mma ? 4 : 2) * in->smCount + chunks - 1) / chunks));
+    // (whole blocks per wave only: a partial second wave would double the run time of this latency-chained kernel)
+    groups = mma ? std::max(1, std::min(count, 4 * in->smCount / chunks))
+                 : std::max(1, std::min(count, (2 * in->smCount + chunks - 1) / chunks));
 }
 
 int crossProductBlocks(const Instance* in, int count) {
