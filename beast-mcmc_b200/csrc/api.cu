@@ -1017,7 +1017,9 @@ int beagleSetPatternPartitions(int instance, int partitionCount, const int* inPa
 static int updateMatricesImpl(Instance* in, const int* eigenIndices, int eigenIndexScalar, const int* rateSets,
                               const int* probabilityIndices, const double* edgeLengths, int count) {
     if (count <= 0) return BEAGLE_SUCCESS;
-    std::vector<int> pack(3 * (size_t)count);
+    // one staged block = one H2D copy: [edge lengths (count doubles)][matrix, eigen, rate-set indices (3 count ints)]
+    std::vector<double> block((size_t)count + (3 * (size_t)count + 1) / 2);
+    int* pack = reinterpret_cast<int*>(block.data() + count);
     for (int k = 0; k < count; ++k) {
         int e = eigenIndices ? eigenIndices[k] : eigenIndexScalar;
         int r = rateSets ? rateSets[k] : 0;
@@ -1028,9 +1030,10 @@ static int updateMatricesImpl(Instance* in, const int* eigenIndices, int eigenIn
         pack[count + k] = e;
         pack[2 * (size_t)count + k] = r;
     }
-    int* dIdx = static_cast<int*>(stage(in, pack.data(), sizeof(int) * pack.size()));
-    double* dLen = static_cast<double*>(stage(in, edgeLengths, sizeof(double) * count));
-    if (dIdx == nullptr || dLen == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+    memcpy(block.data(), edgeLengths, sizeof(double) * count);
+    double* dLen = static_cast<double*>(stage(in, block.data(), sizeof(double) * block.size()));
+    if (dLen == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+    int* dIdx = reinterpret_cast<int*>(dLen + count);
     TimedScope ts(in, T_MATRICES);
     CUDA_OK(launchTransitionMatrices(in, dIdx, dIdx + count, dIdx + 2 * (size_t)count, dLen, count));
     return BEAGLE_SUCCESS;
