@@ -657,10 +657,10 @@ BeagleResourceList* beagleGetResourceList(void) {
     return &gResourceList;
 }
 
-BeagleBenchmarkedResourceList* beagleGetBenchmarkedResourceList(int, int, int, int, int, int*, int, long, long, int,
-                                                                int, int, long) {
-    return nullptr;   // -beagle_auto benchmarking: not implemented this round
-}
+BeagleBenchmarkedResourceList* beagleGetBenchmarkedResourceList(
+    int tipCount, int compactBufferCount, int stateCount, int patternCount, int categoryCount, int* resourceList,
+    int resourceCount, long preferenceFlags, long requirementFlags, int eigenModelCount, int partitionCount,
+    int calculateDerivatives, long benchmarkFlags);   // defined after the entry points it drives
 
 int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBufferCount, int stateCount,
                          int patternCount, int eigenBufferCount, int matrixBufferCount, int categoryCount,
@@ -1539,6 +1539,105 @@ int b200CompressSitePatterns(int resourceNumber, int taxonCount, int siteCount, 
         for (int s = 0; s < siteCount; ++s) outWeights[outSitePatternIndices[s]] += inSiteWeights[s];
     }
     return BEAGLE_SUCCESS;
+}
+
+// -beagle_auto (BDLD:400-434): time a synthetic full evaluation of the stated shape on every candidate resource through
+// the public entry points and return the resources fastest first.  Resource 0 (host) is not implemented and never listed.
+BeagleBenchmarkedResourceList* beagleGetBenchmarkedResourceList(
+    int tipCount, int compactBufferCount, int stateCount, int patternCount, int categoryCount, int* resourceList,
+    int resourceCount, long preferenceFlags, long requirementFlags, int eigenModelCount, int partitionCount,
+    int calculateDerivatives, long benchmarkFlags) {
+    (void)eigenModelCount; (void)partitionCount; (void)calculateDerivatives; (void)compactBufferCount;
+    static std::mutex mu;
+    static std::vector<BeagleBenchmarkedResource> results;
+    static BeagleBenchmarkedResourceList list;
+    static const char* kImpl = "B200-CUDA-Double";
+    std::lock_guard<std::mutex> lock(mu);
+    BeagleResourceList* rl = beagleGetResourceList();
+    if (rl == nullptr || tipCount < 2 || stateCount < 2 || patternCount < 1 || categoryCount < 1) return nullptr;
+    std::vector<int> candidates;
+    if (resourceList != nullptr && resourceCount > 0) {
+        for (int k = 0; k < resourceCount; ++k)
+            if (resourceList[k] >= 1 && resourceList[k] < rl->length &&
+                std::find(candidates.begin(), candidates.end(), resourceList[k]) == candidates.end())
+                candidates.push_back(resourceList[k]);
+    } else {
+        for (int r = 1; r < rl->length; ++r) candidates.push_back(r);
+    }
+    const bool rescale = (benchmarkFlags & 2L) != 0 || (benchmarkFlags & 4L) != 0;    // SCALING_ALWAYS / SCALING_DYNAMIC
+    const int N = tipCount, n = 2 * N - 1, S = stateCount, P = patternCount, C = categoryCount;
+    // synthetic inputs: pseudo-random tip states, a diagonal eigen system (P(t) = diag(exp(-k t / S))), a caterpillar tree
+    std::vector<int> states(P);
+    std::vector<double> evec((size_t)S * S, 0.0), eval(S), ones(std::max(std::max(C, S), P), 1.0), lengths(n - 1, 0.05);
+    for (int i = 0; i < S; ++i) { evec[(size_t)i * S + i] = 1.0; eval[i] = -(double)i / S; }
+    for (double& f : ones) f = 1.0;
+    std::vector<double> freqs(S, 1.0 / S), weights(C, 1.0 / C), rates(C, 1.0);
+    std::vector<int> probIdx(n - 1), ops, scaleIdx;
+    for (int k = 0; k < n - 1; ++k) probIdx[k] = k;
+    for (int k = 0; k < N - 1; ++k) {           // node N+k = (previous node or tip 0, tip k+1)
+        const int dest = N + k, c1 = k == 0 ? 0 : N + k - 1, c2 = k + 1;
+        const int sw = rescale ? k : BEAGLE_OP_NONE;
+        const int tuple[7] = {dest, sw, BEAGLE_OP_NONE, c1, c1, c2, c2};
+        ops.insert(ops.end(), tuple, tuple + 7);
+        scaleIdx.push_back(k);
+    }
+    results.clear();
+    for (int res : candidates) {
+        BeagleBenchmarkedResource br{};
+        br.number = res; br.name = rl->list[res].name; br.description = rl->list[res].description;
+        br.supportFlags = rl->list[res].supportFlags; br.requiredFlags = rl->list[res].requiredFlags;
+        br.implName = const_cast<char*>(kImpl); br.benchedFlags = 0; br.benchmarkResult = 0.0; br.performanceRatio = 0.0;
+        int one[1] = {res};
+        BeagleInstanceDetails det{};
+        const int inst = beagleCreateInstance(N, N - 1, N, S, P, 1, n - 1, C, N + 1, one, 1, preferenceFlags,
+                                              requirementFlags, &det);
+        br.returnCode = inst < 0 ? inst : BEAGLE_SUCCESS;
+        if (inst >= 0) {
+            br.benchedFlags = det.flags;
+            int rc = BEAGLE_SUCCESS;
+            for (int t = 0; t < N && rc == BEAGLE_SUCCESS; ++t) {
+                for (int p = 0; p < P; ++p) states[p] = (int)((1103515245u * (unsigned)(t * 7919 + p) + 12345u) >> 16) % S;
+                rc = beagleSetTipStates(inst, t, states.data());
+            }
+            if (rc == BEAGLE_SUCCESS) rc = beagleSetPatternWeights(inst, ones.data());
+            if (rc == BEAGLE_SUCCESS) rc = beagleSetEigenDecomposition(inst, 0, evec.data(), evec.data(), eval.data());
+            if (rc == BEAGLE_SUCCESS) rc = beagleSetCategoryRates(inst, rates.data());
+            if (rc == BEAGLE_SUCCESS) rc = beagleSetCategoryWeights(inst, 0, weights.data());
+            if (rc == BEAGLE_SUCCESS) rc = beagleSetStateFrequencies(inst, 0, freqs.data());
+            double best = 0.0, logL = 0.0;
+            const int root = n - 1, zero = 0, cum = rescale ? N : BEAGLE_OP_NONE;
+            for (int rep = 0; rep < 6 && rc == BEAGLE_SUCCESS; ++rep) {
+                const auto t0 = std::chrono::steady_clock::now();
+                rc = beagleUpdateTransitionMatrices(inst, 0, probIdx.data(), nullptr, nullptr, lengths.data(), n - 1);
+                if (rc == BEAGLE_SUCCESS)
+                    rc = beagleUpdatePartials(inst, reinterpret_cast<const BeagleOperation*>(ops.data()), N - 1, BEAGLE_OP_NONE);
+                if (rc == BEAGLE_SUCCESS && rescale) {
+                    rc = beagleResetScaleFactors(inst, cum);
+                    if (rc == BEAGLE_SUCCESS) rc = beagleAccumulateScaleFactors(inst, scaleIdx.data(), N - 1, cum);
+                }
+                if (rc == BEAGLE_SUCCESS) {
+                    rc = beagleCalculateRootLogLikelihoods(inst, &root, &zero, &zero, &cum, 1, &logL);
+                    if (rc == BEAGLE_ERROR_FLOATING_POINT) rc = BEAGLE_SUCCESS;      // an underflowing synthetic tree still times
+                }
+                const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                if (rep >= 2 && (best == 0.0 || ms < best)) best = ms;              // two warm-up rounds
+            }
+            br.returnCode = rc;
+            br.benchmarkResult = best;
+            beagleFinalizeInstance(inst);
+        }
+        results.push_back(br);
+    }
+    std::stable_sort(results.begin(), results.end(), [](const BeagleBenchmarkedResource& a, const BeagleBenchmarkedResource& b) {
+        const bool oa = a.returnCode == BEAGLE_SUCCESS, ob = b.returnCode == BEAGLE_SUCCESS;
+        return oa != ob ? oa : (oa && a.benchmarkResult < b.benchmarkResult);
+    });
+    for (BeagleBenchmarkedResource& r : results)
+        r.performanceRatio = (results[0].benchmarkResult > 0.0 && r.returnCode == BEAGLE_SUCCESS)
+                                 ? r.benchmarkResult / results[0].benchmarkResult : 0.0;
+    list.list = results.data();
+    list.length = (int)results.size();
+    return list.length > 0 ? &list : nullptr;
 }
 
 void* b200HostAlloc(long bytes) {

@@ -70,9 +70,52 @@ NATIVE(jobjectArray, getResourceList)(JNIEnv* env, jobject) {
     return out;
 }
 
-NATIVE(jobjectArray, getBenchmarkedResourceList)(JNIEnv*, jobject, jint, jint, jint, jint, jint, jintArray, jint, jlong,
-                                                 jlong, jint, jint, jint, jlong) {
-    return nullptr;     // -beagle_auto: not implemented this round
+NATIVE(jobjectArray, getBenchmarkedResourceList)(JNIEnv* env, jobject, jint tipCount, jint compactBufferCount,
+                                                 jint stateCount, jint patternCount, jint categoryCount,
+                                                 jintArray resourceList, jint resourceCount, jlong preferenceFlags,
+                                                 jlong requirementFlags, jint eigenModelCount, jint partitionCount,
+                                                 jint calculateDerivatives, jlong benchmarkFlags) {
+    IntIn res(env, resourceList);
+    BeagleBenchmarkedResourceList* bl = beagleGetBenchmarkedResourceList(
+        tipCount, compactBufferCount, stateCount, patternCount, categoryCount, res.mut(), res.p ? resourceCount : 0,
+        (long)preferenceFlags, (long)requirementFlags, eigenModelCount, partitionCount, calculateDerivatives,
+        (long)benchmarkFlags);
+    if (bl == nullptr) return nullptr;
+    jclass cls = env->FindClass("beagle/BenchmarkedResourceDetails");
+    if (cls == nullptr) return nullptr;
+    jmethodID ctor = env->GetMethodID(cls, "<init>", "(I)V");
+    jmethodID setResourceNumber = env->GetMethodID(cls, "setResourceNumber", "(I)V");
+    jmethodID setName = env->GetMethodID(cls, "setName", "(Ljava/lang/String;)V");
+    jmethodID setDesc = env->GetMethodID(cls, "setDescription", "(Ljava/lang/String;)V");
+    jmethodID setSupport = env->GetMethodID(cls, "setSupportFlags", "(J)V");
+    jmethodID setRequired = env->GetMethodID(cls, "setRequiredFlags", "(J)V");
+    jmethodID setReturnCode = env->GetMethodID(cls, "setReturnCode", "(I)V");
+    jmethodID setImplName = env->GetMethodID(cls, "setImplName", "(Ljava/lang/String;)V");
+    jmethodID setBenched = env->GetMethodID(cls, "setBenchedFlags", "(J)V");
+    jmethodID setResult = env->GetMethodID(cls, "setBenchmarkResult", "(D)V");
+    jmethodID setRatio = env->GetMethodID(cls, "setPerformanceRatio", "(D)V");
+    if (!ctor || !setResourceNumber || !setName || !setDesc || !setSupport || !setRequired || !setReturnCode ||
+        !setImplName || !setBenched || !setResult || !setRatio)
+        return nullptr;
+    jobjectArray out = env->NewObjectArray(bl->length, cls, nullptr);
+    for (int i = 0; i < bl->length; ++i) {
+        const BeagleBenchmarkedResource& b = bl->list[i];
+        jobject r = env->NewObject(cls, ctor, (jint)i);
+        jstring n = env->NewStringUTF(b.name), d = env->NewStringUTF(b.description), im = env->NewStringUTF(b.implName);
+        env->CallVoidMethod(r, setResourceNumber, (jint)b.number);
+        env->CallVoidMethod(r, setName, n);
+        env->CallVoidMethod(r, setDesc, d);
+        env->CallVoidMethod(r, setSupport, (jlong)b.supportFlags);
+        env->CallVoidMethod(r, setRequired, (jlong)b.requiredFlags);
+        env->CallVoidMethod(r, setReturnCode, (jint)b.returnCode);
+        env->CallVoidMethod(r, setImplName, im);
+        env->CallVoidMethod(r, setBenched, (jlong)b.benchedFlags);
+        env->CallVoidMethod(r, setResult, (jdouble)b.benchmarkResult);
+        env->CallVoidMethod(r, setRatio, (jdouble)b.performanceRatio);
+        env->SetObjectArrayElement(out, i, r);
+        env->DeleteLocalRef(n); env->DeleteLocalRef(d); env->DeleteLocalRef(im); env->DeleteLocalRef(r);
+    }
+    return out;
 }
 
 NATIVE(jint, createInstance)(JNIEnv* env, jobject, jint tipCount, jint partialsBufferCount, jint compactBufferCount,

@@ -22,6 +22,7 @@ struct FakeObj {
     std::vector<FakeObj*> elems;
     std::map<std::string, std::string> sfields;
     std::map<std::string, long long> ifields;
+    std::map<std::string, double> dfields;
 };
 struct FakeMethod { std::string name, sig; };
 
@@ -39,6 +40,7 @@ static jmethodID f_GetMethodID(JNIEnv*, jclass, const char* name, const char* si
 static void applyCall(FakeObj* obj, FakeMethod* m, va_list ap) {
     if (m->sig == "(I)V") obj->ifields[m->name] = va_arg(ap, jint);
     else if (m->sig == "(J)V") obj->ifields[m->name] = va_arg(ap, jlong);
+    else if (m->sig == "(D)V") obj->dfields[m->name] = va_arg(ap, jdouble);
     else if (m->sig == "(Ljava/lang/String;)V") { FakeObj* s = O(va_arg(ap, jobject)); obj->sfields[m->name] = s ? s->str : ""; }
     else { fprintf(stderr, "fake_jvm: unsupported signature %s\n", m->sig.c_str()); exit(2); }
 }
@@ -121,6 +123,17 @@ int main(int argc, char** argv) {
     for (FakeObj* r : rl->elems)
         printf("resource %lld name=%s flags=%lld\n", r->ifields["<init>"], r->sfields["setName"].c_str(), r->ifields["setFlags"]);
     if (std::string(argv[2]) == "info") return 0;
+    if (std::string(argv[2]) == "auto") {
+        // BDLD:413-426 (-beagle_auto): the benchmarked list, fastest first
+        typedef jobjectArray (*bench_t)(JNIEnv*, jobject, jint, jint, jint, jint, jint, jintArray, jint, jlong, jlong, jint, jint, jint, jlong);
+        jobjectArray arr = sym<bench_t>(h, "getBenchmarkedResourceList")(env, self, 16, 16, 4, 500, 4, nullptr, 0, 0, 0, 1, 1, 0, 1);
+        if (arr == nullptr) { printf("benchmarked null\n"); return 0; }
+        for (FakeObj* r : O(arr)->elems)
+            printf("benchmarked %lld resource=%lld name=%s impl=%s rc=%lld ms=%.4f ratio=%.3f\n", r->ifields["<init>"],
+                   r->ifields["setResourceNumber"], r->sfields["setName"].c_str(), r->sfields["setImplName"].c_str(),
+                   r->ifields["setReturnCode"], r->dfields["setBenchmarkResult"], r->dfields["setPerformanceRatio"]);
+        return 0;
+    }
 
     // ---- tiny test -----------------------------------------------------------------------------
     FILE* f = fopen(argv[3], "r");

@@ -114,3 +114,16 @@ def test_fake_jvm_gradient_natives(jni, tmp_path):
     assert np.allclose([float(v) for v in edge], s1, rtol=1e-8, atol=1e-8), (edge, s1)
     assert np.allclose([float(v) for v in got_cross], cross, rtol=1e-7, atol=2e-8), (got_cross, cross)
     assert f"logL {expected:.5f} rc 0" in out
+
+
+@pytest.mark.gpu
+def test_fake_jvm_beagle_auto(jni):
+    """-beagle_auto (BDLD:400-434): getBenchmarkedResourceList returns the GPU resources, fastest first, never resource 0."""
+    lib, exe = jni
+    out = subprocess.run([exe, lib, "auto"], capture_output=True, text=True, check=True).stdout
+    rows = re.findall(r"benchmarked (\d+) resource=(\d+) name=(.*) impl=B200-CUDA-Double rc=0 ms=([0-9.]+) ratio=([0-9.]+)", out)
+    assert rows, out
+    assert [int(r[0]) for r in rows] == list(range(len(rows)))
+    assert all(int(r[1]) >= 1 for r in rows) and float(rows[0][4]) == 1.0
+    ms = [float(r[3]) for r in rows]
+    assert ms == sorted(ms) and ms[0] > 0.0
