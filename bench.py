@@ -47,6 +47,8 @@ WORKLOADS = {
                                      scaling=True, data="gtr_g4_1000x10k"),
     # configs[2]: codon model on the dense-contraction path
     "codon_mg94_500x5k": dict(taxa=500, patterns=5000, states=61, categories=1, rootHeight=0.1, treeSeed=2),
+    # amino-acid shape (20 states, G4): the tensor path's NT=3 instance, on the memory side of the roofline
+    "aa20_g4_500x5k": dict(taxa=500, patterns=5000, states=20, categories=4, rootHeight=0.3, treeSeed=4),
     "codon_mg94_500x5k_g4": dict(taxa=500, patterns=5000, states=61, categories=4, rootHeight=0.1, treeSeed=2),
     # configs[0]-like latency case (benchmark1.xml shape: 1441 taxa, 593 patterns, HKY, no gamma)
     "hky_1441x593": dict(taxa=1441, patterns=593, states=4, categories=1, rootHeight=0.1, treeSeed=1441),
