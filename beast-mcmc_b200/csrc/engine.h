@@ -127,7 +127,7 @@ struct Instance {
     long timedLaunches[T_CLASSES] = {0, 0, 0};
 
     // tuning knobs (environment overridable, see api.cu)
-    size_t walkSmemConfigured = 0, genericSmemConfigured = 0, mmaSmemConfigured[2] = {0, 0};
+    size_t walkSmemConfigured = 0, genericSmemConfigured = 0, mmaSmemConfigured[4] = {0, 0, 0, 0};
     int walkBlock = 128;
     int walkVariant = 0;
     std::vector<CachedPlan> planCache;

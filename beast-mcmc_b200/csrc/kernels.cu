@@ -842,14 +842,17 @@ __device__ __forceinline__ void bulkCopyG2S(void* smemDst, const void* gmemSrc, 
 // the matrices sit in global memory already in the padded [Sp][Sp+4] shape the fragment loads want, so each is one
 // contiguous transfer; everyone else waits on the mbarrier and spends no issue slots on staging.  Single buffer: the
 // other resident blocks of the SM cover the copy (measured faster than a double buffer at one block per SM).
-template <int NT, int WARPS, bool PRE>
+template <int NT, int WARPS, bool PRE, bool MULTI>
 __global__ void __launch_bounds__(WARPS * 32, 3)
-k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int C, int Ppad, int logScalers) {
+k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int C, int Ppad, int logScalers, int cbArg) {
+    const int cb = MULTI ? cbArg : 1;               // MULTI = false: one category per staging round, folded at compile time
     constexpr int Sp = 8 * NT;
     constexpr int LD = Sp + 4;                       // shared-memory row stride (doubles)
     constexpr int MATSZ = Sp * LD;
     constexpr unsigned MATBYTES = MATSZ * sizeof(double);
-    extern __shared__ __align__(128) double smw[];   // [2 matrices][Sp][LD]
+    // [child 1: cb categories][child 2: cb categories] x [Sp][LD]; cb = categories staged per bulk copy (small state
+    // counts stage all of an op's categories at once: one barrier round trip per op instead of one per category)
+    extern __shared__ __align__(128) double smw[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -869,24 +872,26 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
     bool act[2] = {false, false};
     double rowMax[2] = {0.0, 0.0};
     for (int flat = 0; flat < total; ++flat) {
-        if (tid == 0) {
-            const DevOp* o = ops + range.x + flat / C;
-            const int cs = flat % C;
-            // pre-order ops contract over the ROW index of the node's own matrix: stage its transposed copy
-            const double* g1 = o->m1 + (PRE ? mTp : mRow) + (size_t)cs * MATSZ;
-            const double* g2 = o->m2 + mRow + (size_t)cs * MATSZ;
-            // the generic-proxy reads of the previous pair (ordered by the barrier that ended it) precede these writes
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbarExpectTx(&bar, 2 * MATBYTES);
-            bulkCopyG2S(smw, g1, MATBYTES, &bar);
-            bulkCopyG2S(smw + MATSZ, g2, MATBYTES, &bar);
+        const int c = flat % C, cg = c % cb;
+        if (cg == 0) {
+            if (tid == 0) {
+                const DevOp* o = ops + range.x + flat / C;
+                const unsigned bytes = (unsigned)min(cb, C - c) * MATBYTES;       // consecutive categories are contiguous
+                // pre-order ops contract over the ROW index of the node's own matrix: stage its transposed copy
+                const double* g1 = o->m1 + (PRE ? mTp : mRow) + (size_t)c * MATSZ;
+                const double* g2 = o->m2 + mRow + (size_t)c * MATSZ;
+                // the generic-proxy reads of the previous group (ordered by the barrier that ended it) precede these writes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbarExpectTx(&bar, 2 * bytes);
+                bulkCopyG2S(smw, g1, bytes, &bar);
+                bulkCopyG2S(smw + (size_t)cb * MATSZ, g2, bytes, &bar);
+            }
+            mbarWait(&bar, parity);
+            parity ^= 1;
         }
-        mbarWait(&bar, parity);
-        parity ^= 1;
         const DevOp op = ops[range.x + flat / C];
-        const int c = flat % C;
-        const double* P1 = smw;
-        const double* P2 = P1 + MATSZ;
+        const double* P1 = smw + (size_t)cg * MATSZ;
+        const double* P2 = smw + (size_t)(cb + cg) * MATSZ;
         if (c == 0) {
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -1064,21 +1069,33 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
         }
         // (a) every warp is done with this buffer before the copy issued next iteration overwrites it,
         // (b) rows written by other lanes of this warp become visible to the next op's A-fragment loads
-        __syncthreads();
+        if (cg == cb - 1 || c == C - 1) __syncthreads();
     }
 }
 
 template <int NT, int WARPS, bool PRE = false>
 static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     constexpr int Sp = 8 * NT;
-    const size_t smem = 2 * (size_t)Sp * (Sp + 4) * sizeof(double);
-    if (smem > in->mmaSmemConfigured[PRE ? 1 : 0]) {
-        cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        in->mmaSmemConfigured[PRE ? 1 : 0] = smem;
-    }
+    const size_t pair = 2 * (size_t)Sp * (Sp + 4) * sizeof(double);
+    // as many categories per staging round as keep three blocks resident per SM (72 KB each)
+    const int cb = (int)std::max<size_t>(1, std::min<size_t>((size_t)in->C, (72 * 1024) / pair));
+    const size_t smem = pair * cb;
     dim3 grid((maxWindow + WARPS * 16 - 1) / (WARPS * 16), nSubs);
-    k_walk_mma<NT, WARPS, PRE><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0);
+    if (cb == 1) {
+        if (smem > in->mmaSmemConfigured[PRE ? 1 : 0]) {
+            cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, PRE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            in->mmaSmemConfigured[PRE ? 1 : 0] = smem;
+        }
+        k_walk_mma<NT, WARPS, PRE, false><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0, 1);
+    } else {
+        if (smem > in->mmaSmemConfigured[PRE ? 3 : 2]) {
+            cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, PRE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            in->mmaSmemConfigured[PRE ? 3 : 2] = smem;
+        }
+        k_walk_mma<NT, WARPS, PRE, true><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0, cb);
+    }
     return cudaGetLastError();
 }
 
