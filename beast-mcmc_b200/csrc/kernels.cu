@@ -1205,6 +1205,72 @@ k_edge_derivatives(const EdgeRef* __restrict__ edges, const double* __restrict__
     if (tid == 0) { outSum[blockIdx.x] = red1[0]; outSumSq[blockIdx.x] = red2[0]; }
 }
 
+// 4-state form: grid (256-pattern chunks, edges), a thread owns one (edge, pattern); the C differential matrices of the
+// edge sit in shared memory, the 2 C cell loads of a thread are issued four categories at a time.
+__global__ void __launch_bounds__(256)
+k_edge_derivatives4(const EdgeRef* __restrict__ edges, const double* __restrict__ weights,
+                    const double* __restrict__ patternWeights, int C, int P, int Ppad, int matCP,
+                    double* __restrict__ outPerPattern, double* __restrict__ partial) {
+    extern __shared__ double sD[];                  // [C][j][k]
+    __shared__ double red[8][2];
+    const EdgeRef e = edges[blockIdx.y];
+    const int tid = threadIdx.x, p = blockIdx.x * 256 + tid;
+    for (int q = tid; q < C * 16; q += 256) {
+        const int c = q >> 4, j = (q >> 2) & 3, k = q & 3;
+        sD[q] = e.D[((size_t)k * matCP + c) * 4 + j];
+    }
+    __syncthreads();
+    double s1 = 0.0, s2 = 0.0;
+    if (p < P) {
+        const int s = e.states ? e.states[p] : -1;
+        double num = 0.0, den = 0.0;
+        for (int c0 = 0; c0 < C; c0 += 4) {
+            double a[4][4], b[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t off = ((size_t)min(c0 + u, C - 1) * Ppad + p) * 4;
+                ldg256_ro(e.pre + off, a[u]);
+                if (e.post) ldg256_ro(e.post + off, b[u]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) b[u][j] = (s >= 4 || s == j) ? 1.0 : 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (c0 + u >= C) break;
+                const double* D = sD + (c0 + u) * 16;
+                double nc = 0.0, dc = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double v = D[j * 4] * b[u][0] + D[j * 4 + 1] * b[u][1] + D[j * 4 + 2] * b[u][2] + D[j * 4 + 3] * b[u][3];
+                    nc += a[u][j] * v;
+                    dc += a[u][j] * b[u][j];
+                }
+                num += weights[c0 + u] * nc;
+                den += weights[c0 + u] * dc;
+            }
+        }
+        const double d = num / den;
+        if (outPerPattern) outPerPattern[(size_t)blockIdx.y * P + p] = d;
+        s1 = patternWeights[p] * d;
+        s2 = patternWeights[p] * d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((tid & 31) == 0) { red[tid >> 5][0] = s1; red[tid >> 5][1] = s2; }
+    __syncthreads();
+    if (tid < 2) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += red[w][tid];
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + tid] = r;
+    }
+}
+
 // Tensor-pipe form for the state counts of the DMMA walk (Sp = 8 NT): block = 4 warps x 16 patterns of ONE edge.
 // Per category the row-major D_c is staged like a transition matrix, v = D_c post is the same m8n8k4 contraction as a
 // post-order child term, and the two dot products with the pre-order partial are taken in the accumulator layout.
@@ -1351,13 +1417,24 @@ static cudaError_t launchEdgeMmaT(Instance* in, const EdgeRef* dEdges, int count
 
 // doubles of workspace the tensor-pipe form needs (0 = this state count uses the plain kernel)
 size_t edgeDerivativeWorkspace(const Instance* in, int count) {
+    if (count > 65535) return 0;
+    if (in->matCP > 0 && in->S == 4) return (size_t)count * ((in->P + 255) / 256) * 2;
     const int nt = in->Sp / 8;
-    const bool mma = in->genericMma && in->matCP == 0 && in->Sp % 8 == 0 && (nt >= 1 && nt <= 4 || nt == 8) && count <= 65535;
+    const bool mma = in->genericMma && in->matCP == 0 && in->Sp % 8 == 0 && ((nt >= 1 && nt <= 4) || nt == 8);
     return mma ? (size_t)count * ((in->P + 63) / 64) * 2 : 0;
 }
 
 cudaError_t launchEdgeDerivatives(Instance* in, const EdgeRef* dEdges, int count, const double* weights,
                                   double* outPerPattern, double* outSum, double* outSumSq, double* partial) {
+    if (partial != nullptr && in->matCP > 0) {
+        const int chunks = (in->P + 255) / 256;
+        k_edge_derivatives4<<<dim3(chunks, count), 256, sizeof(double) * 16 * in->C, in->stream>>>(
+            dEdges, weights, in->dPatternWeights, in->C, in->P, in->Ppad, in->matCP, outPerPattern, partial);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        k_edge_sum<<<(count + 127) / 128, 128, 0, in->stream>>>(partial, chunks, count, outSum, outSumSq);
+        return cudaGetLastError();
+    }
     if (partial != nullptr) {
         switch (in->Sp / 8) {
             case 1: return launchEdgeMmaT<1>(in, dEdges, count, weights, outPerPattern, outSum, outSumSq, partial);
@@ -1407,22 +1484,30 @@ k_cross4(const EdgeRef* __restrict__ edges, int count, const double* __restrict_
             double num[16], den = 0.0;
 #pragma unroll
             for (int q = 0; q < 16; ++q) num[q] = 0.0;
-            for (int c = 0; c < C; ++c) {
-                const size_t off = ((size_t)c * Ppad + p) * 4;
-                double a[4], b[4];
-                ldg256(r.pre + off, a);
-                if (r.post) ldg256(r.post + off, b);
-                else {
+            // four categories per round, clamped + zero-weighted past C: all 8 loads of a round are in flight together
+            for (int c0 = 0; c0 < C; c0 += 4) {
+                double a[4][4], b[4][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] = (s >= 4 || s == j) ? 1.0 : 0.0;
+                for (int u = 0; u < 4; ++u) {
+                    const size_t off = ((size_t)min(c0 + u, C - 1) * Ppad + p) * 4;
+                    ldg256_ro(r.pre + off, a[u]);
+                    if (r.post) ldg256_ro(r.post + off, b[u]);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b[u][j] = (s >= 4 || s == j) ? 1.0 : 0.0;
+                    }
                 }
-                const double wc = weights[c], f = wc * rates[c];
-                den += wc * (a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double fa = f * a[i];
+                for (int u = 0; u < 4; ++u) {
+                    const bool live = c0 + u < C;
+                    const double wc = live ? weights[c0 + u] : 0.0, f = live ? wc * rates[c0 + u] : 0.0;
+                    den += wc * (a[u][0] * b[u][0] + a[u][1] * b[u][1] + a[u][2] * b[u][2] + a[u][3] * b[u][3]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) num[i * 4 + j] += fa * b[j];
+                    for (int i = 0; i < 4; ++i) {
+                        const double fa = f * a[u][i];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) num[i * 4 + j] += fa * b[u][j];
+                    }
                 }
             }
             const double sc = wp * r.len / den;
@@ -1683,7 +1768,7 @@ static void crossGeometry(const Instance* in, int count, int& pch, int& chunks, 
     // the tensor form is a chain of short dependent phases per edge: fill every SM with 4 resident blocks
     // (whole blocks per wave only: a partial second wave would double the run time of this latency-chained kernel)
     groups = mma ? std::max(1, std::min(count, 4 * in->smCount / chunks))
-                 : std::max(1, std::min(count, (2 * in->smCount + chunks - 1) / chunks));
+                 : std::max(1, std::min(count, ((four ? 4 : 2) * in->smCount + chunks - 1) / chunks));
 }
 
 int crossProductBlocks(const Instance* in, int count) {
