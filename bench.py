@@ -538,6 +538,10 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_walk4 (updatePartials, whole op list per launch)"
                      if S <= 4 else "k_walk_generic", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     # DRAM-side view of the same launches: measured bytes (ncu) over the live time.  frac counts ALGORITHMIC
+                     # bytes, of which children re-read from L2 never reach HBM -- it can exceed 1; dram_frac cannot.
+                     "dram_achieved": (traffic / (k_avg_ms * 1e-3) / 1e9) if traffic else None,
+                     "dram_frac": (traffic / (k_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
                      "algorithmic_bytes_per_step": byt, "algorithmic_flops_per_step": flo,
                      "gflops": flo / (k_avg_ms * 1e-3) / 1e9, "partials_ms_per_step": k_avg_ms,
                      "launches_per_step": k_n / args.steps,
