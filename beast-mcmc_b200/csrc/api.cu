@@ -303,6 +303,77 @@ void planLevels(const std::vector<HostOp>& ops, int nBuffers, Plan& plan) {
     plan.phaseStart.push_back((int)plan.subs.size());
 }
 
+// Pre-order lists, the mirror image of planPhases: op(node) needs op(parent) (its c1 is the parent's destination) and
+// nothing else from this list, so the ops form an OUT-forest.  Subtrees of that forest are cut bottom-up exactly like the
+// post-order plan ("all maximal subtrees with <= T ops", then again on what is left) and the phases run in REVERSE order
+// of extraction: the crown first, the many independent subtrees last.  Inside a subtree ops run in depth-first pre-order,
+// so the op after a node is its first child and finds pre[parent] in the walking thread's registers.
+// Anything the forest model does not cover (double write, read-before-write, a c2 produced in this list) -> planLevels.
+void planPreorderPhases(const std::vector<HostOp>& ops, int nBuffers, int fixedT, int wantSubs, int minT,
+                        int smallRemainder, Plan& plan) {
+    const int n = (int)ops.size();
+    std::vector<int> writer(nBuffers, -1), parent(n, -1);
+    bool ok = n >= 2;
+    for (int k = 0; k < n && ok; ++k) { ok = writer[ops[k].dest] < 0; writer[ops[k].dest] = k; }
+    for (int k = 0; k < n && ok; ++k) {
+        const int a = writer[ops[k].c1];
+        ok = writer[ops[k].c2] < 0 && (a < 0 || a < k) && ops[k].dest != ops[k].c1 && ops[k].dest != ops[k].c2;
+        parent[k] = a;
+    }
+    if (!ok) { planLevels(ops, nBuffers, plan); return; }
+    std::vector<std::vector<int>> kids(n);
+    for (int k = 0; k < n; ++k) if (parent[k] >= 0) kids[parent[k]].push_back(k);
+    std::vector<char> alive(n, 1);
+    std::vector<int> size(n), stack;
+    std::vector<std::vector<int>> phases;          // roots of the subtrees of each extracted phase
+    int remaining = n;
+    while (remaining > 0) {
+        const int T = fixedT > 0 ? fixedT : (remaining <= smallRemainder ? remaining : std::max(minT, (remaining + wantSubs - 1) / wantSubs));
+        for (int k = n - 1; k >= 0; --k) {          // children have larger indices than their parent
+            if (!alive[k]) continue;
+            size[k] = 1;
+            for (int c : kids[k]) if (alive[c]) size[k] += size[c];
+        }
+        std::vector<int> roots;
+        for (int r = 0; r < n; ++r)
+            if (alive[r] && size[r] <= T && !(parent[r] >= 0 && alive[parent[r]] && size[parent[r]] <= T)) roots.push_back(r);
+        for (int r : roots) {                       // retire after the snapshot was judged
+            stack.assign(1, r);
+            while (!stack.empty()) {
+                const int k = stack.back(); stack.pop_back();
+                if (!alive[k]) continue;
+                alive[k] = 0; --remaining;
+                for (int c : kids[k]) if (alive[c]) stack.push_back(c);
+            }
+        }
+        phases.push_back(std::move(roots));
+    }
+    // emit: last extracted phase first; membership of a subtree = the ops retired with its root
+    std::vector<int> phaseOf(n, -1), rootOf(n, -1);
+    for (int ph = 0; ph < (int)phases.size(); ++ph)
+        for (int r : phases[ph]) { phaseOf[r] = ph; rootOf[r] = r; }
+    for (int k = 0; k < n; ++k)                      // parents precede children: inherit unless k is itself a root
+        if (rootOf[k] < 0) { rootOf[k] = rootOf[parent[k]]; phaseOf[k] = phaseOf[parent[k]]; }
+    plan.order.clear(); plan.order.reserve(n);
+    plan.subs.clear(); plan.phaseStart.assign(1, 0);
+    for (int ph = (int)phases.size() - 1; ph >= 0; --ph) {
+        for (int r : phases[ph]) {
+            const int begin = (int)plan.order.size();
+            stack.assign(1, r);
+            while (!stack.empty()) {                 // depth-first pre-order restricted to this subtree
+                const int k = stack.back(); stack.pop_back();
+                plan.order.push_back(k);
+                for (int q = (int)kids[k].size() - 1; q >= 0; --q)
+                    if (rootOf[kids[k][q]] == r) stack.push_back(kids[k][q]);
+            }
+            plan.subs.push_back(Sub{begin, (int)plan.order.size(), 0, 0});
+        }
+        std::stable_sort(plan.subs.begin() + plan.phaseStart.back(), plan.subs.end(),
+                         [](const Sub& a, const Sub& b) { return (a.end - a.begin) > (b.end - b.begin); });
+        plan.phaseStart.push_back((int)plan.subs.size());
+    }
+}
+
 // launch the phases of a prepared plan (device-resident op records + subtree table)
 cudaError_t launchPlan(Instance* in, const void* dOps, const void* dSubs, const std::vector<int>& phaseStart,
                        const std::vector<int>& phaseDepth, bool fourPath, int maxWindow, bool preOrder) {
@@ -393,7 +464,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             return std::max(1, in->phaseOversub * ((in->smCount * warpsPerSM + warpsPerSub - 1) / warpsPerSub));
         };
         if (!byPartition) {
-            if (hops[0].kind == 1) planLevels(hops, in->nBuffers, plan);
+            if (hops[0].kind == 1 && in->prePhases) planPreorderPhases(hops, in->nBuffers, in->phaseT, wantSubsFor(in->Ppad), in->phaseTmin, in->phaseSmall, plan);
+            else if (hops[0].kind == 1) planLevels(hops, in->nBuffers, plan);
             else planPhases(hops, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(in->Ppad), in->phaseTmin, in->phaseSmall, plan);
             for (Sub& sb : plan.subs) { sb.pBase = 0; sb.pLimit = in->Ppad; }
         } else {
@@ -410,7 +482,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
                 for (size_t q = 0; q < sub.size(); ++q) sub[q] = hops[members[part][q]];
                 Plan pl;
                 const int window = in->partEnd[part] - in->partBegin[part];
-                if (sub[0].kind == 1) planLevels(sub, in->nBuffers, pl);
+                if (sub[0].kind == 1 && in->prePhases) planPreorderPhases(sub, in->nBuffers, in->phaseT, wantSubsFor(std::max(1, window)), in->phaseTmin, in->phaseSmall, pl);
+                else if (sub[0].kind == 1) planLevels(sub, in->nBuffers, pl);
                 else planPhases(sub, in->nBuffers, in->reorder != 0, in->phaseT, wantSubsFor(std::max(1, window)), in->phaseTmin, in->phaseSmall, pl);
                 base.push_back((int)plan.order.size());
                 for (int idx : pl.order) plan.order.push_back(members[part][idx]);
@@ -537,12 +610,11 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             d.pfA = d.pfB = 0; d.pfM1 = d.pfM2 = -1;
             // register forwarding: inside one subtree walk a thread re-reads, as a child, exactly the cell it wrote for
             // the previous op -- flag it (bit 1), with that child moved to position 1 (the product commutes exactly)
-            if (in->forward && !preOrder && !(maxDepth > 0 && subStack[subOfPos[pos]]) &&
-                pos > plan.subs[subOfPos[pos]].begin) {
+            if (in->forward && !(maxDepth > 0 && subStack[subOfPos[pos]]) && pos > plan.subs[subOfPos[pos]].begin) {
                 const Op4& pv = ops4[pos - 1];
                 if (pv.pBegin == d.pBegin && pv.pEnd == d.pEnd) {
-                    if (!t1 && d.c1 == pv.dest) d.pad_ |= 2;
-                    else if (!t2 && d.c2 == pv.dest) { std::swap(d.c1, d.c2); std::swap(d.m1, d.m2); d.pad_ |= 2; }
+                    if (!t1 && d.c1 == pv.dest) d.pad_ |= 2;            // pre-order: pre[parent] is the previous result
+                    else if (!preOrder && !t2 && d.c2 == pv.dest) { std::swap(d.c1, d.c2); std::swap(d.m1, d.m2); d.pad_ |= 2; }
                 }
             }
         } else {
@@ -727,6 +799,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->forward = envInt("B200_FORWARD", 1);
     in->lookahead = envInt("B200_LOOKAHEAD", 1);
     in->useGraphs = envInt("B200_GRAPHS", 1);
+    in->prePhases = envInt("B200_PRE_PHASES", 1);
     in->planCacheSize = std::max(0, std::min(16, envInt("B200_PLAN_CACHE", 4)));
     in->planCache.reserve(16);
     in->thinR1 = envInt("B200_THIN_R1", 1);
@@ -1480,7 +1553,8 @@ int b200DebugPlan(const int* operations, int operationCount, int bufferCount, in
     }
     Plan plan;
     if (operationCount == 0) { outCounts[0] = outCounts[1] = 0; return BEAGLE_SUCCESS; }
-    if (preOrder) planLevels(hops, bufferCount, plan);
+    if (preOrder == 2) planLevels(hops, bufferCount, plan);
+    else if (preOrder) planPreorderPhases(hops, bufferCount, fixedT, std::max(1, wantSubs), std::max(1, minT), smallRemainder, plan);
     else planPhases(hops, bufferCount, true, fixedT, std::max(1, wantSubs), std::max(1, minT), smallRemainder, plan);
     for (int k = 0; k < operationCount; ++k) outOrder[k] = plan.order[k];
     for (size_t q = 0; q < plan.subs.size(); ++q) { outSubs[2 * q] = plan.subs[q].begin; outSubs[2 * q + 1] = plan.subs[q].end; }

@@ -105,6 +105,7 @@ struct Instance {
     double* dBlockSums = nullptr;
     double* dOut = nullptr;                   // [maxPartitions + 1]
     unsigned int* dCounter = nullptr;
+    int prePhases = 1;                        // pre-order lists as phased subtree walks (0: one launch per depth level)
     int useGraphs = 1;                        // B200_GRAPHS
     int lookahead = 1;                        // L1 prefetch of the next op's operands (B200_LOOKAHEAD)
     int forward = 1;                          // register forwarding between consecutive ops of a walk (B200_FORWARD)

@@ -399,18 +399,25 @@ k_walk4(const WalkArgs A) {
         } else {
             // pre-order op: q = pre[parent] (*) (M_sib post[sib]) at the parent, then down the node's own branch
             // with the transposed matrix: pre[node][j] = sum_i q[i] M_node[i][j]
-            childTerm<CP, R, false, true>(A, cur.c2, cur.m2, 0xFF, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, d);
+            // (depth-first order inside a subtree walk: when this node is the first child of the previous op's node,
+            // pre[parent] is still in d -- flag bit 1 -- and is not re-read)
+            double v[R][4];
+            childTerm<CP, R, false, true>(A, cur.c2, cur.m2, 0xFF, moff, off0, p0, catValid, cur.pBegin, cur.pEnd, stackMem, nthreads, v);
             Mat4 M1;
             loadMat<CP>(A.mats + (size_t)cur.m1 * A.matStride + moff, M1);
             const double* xg = A.partials + (size_t)cur.c1 * A.stride + off0;
+            const bool fromRegisters = (cur.pad_ & 2) != 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int p = p0 + r * G;
                 double x[4] = {0.0, 0.0, 0.0, 0.0};
-                if (catValid && p >= cur.pBegin && p < cur.pEnd) ldg256(xg + (size_t)r * G * 4, x);
+                if (fromRegisters) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = d[r][i];
+                } else if (catValid && p >= cur.pBegin && p < cur.pEnd) ldg256(xg + (size_t)r * G * 4, x);
                 double q[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) q[i] = x[i] * d[r][i];
+                for (int i = 0; i < 4; ++i) q[i] = x[i] * v[r][i];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) d[r][j] = M1.r[j][0] * q[0] + M1.r[j][1] * q[1] + M1.r[j][2] * q[2] + M1.r[j][3] * q[3];
             }
@@ -639,7 +646,7 @@ template <int CP>
 static cudaError_t launchWalk4T(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder) {
     // a thin phase (few walks in flight) is latency-bound: one pattern group per thread gives 4x the warps per op
     const long walks = (long)nSubs * ((maxWindow + (32 / CP) * in->walkR - 1) / ((32 / CP) * in->walkR));
-    if (in->thinR1 && !preOrder && stackDepth == 0 && walks < (long)in->smCount * 8)
+    if (in->thinR1 && stackDepth == 0 && walks < (long)in->smCount * 8)
         return launchWalk4R<CP, 1>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);
     switch (in->walkR) {
         case 4: return launchWalk4R<CP, 4>(in, dOps, dSubs, nSubs, stackDepth, maxWindow, preOrder);

@@ -333,7 +333,8 @@ BEAGLE_DLLEXPORT int b200CompressSitePatterns(int resourceNumber, int taxonCount
 /* Host-logic test hook (no CUDA): the engine's execution plan for a 7-int-per-op list.  outOrder[n] = execution
  * position -> caller index; outSubs = (begin,end) position pairs of the independent subtree walks, grouped by phase;
  * outPhaseStart = index of each phase's first subtree (phases+1 entries); outCounts = {subtrees, phases}.
- * Array capacities: outSubs 2n ints, outPhaseStart n+1 ints. */
+ * Array capacities: outSubs 2n ints, outPhaseStart n+1 ints.  preOrder: 0 = post-order list, 1 = pre-order list planned
+ * as phased subtree walks of the out-forest, 2 = pre-order list planned as one launch per depth level. */
 BEAGLE_DLLEXPORT int b200DebugPlan(const int* operations, int operationCount, int bufferCount, int fixedT, int wantSubs,
                                    int minT, int smallRemainder, int preOrder, int* outOrder, int* outSubs,
                                    int* outPhaseStart, int* outCounts);

@@ -1,5 +1,5 @@
 """Host logic of updatePartials (no GPU): the execution plan the engine derives from an operation list --
-phases of disjoint subtrees for post-order lists, depth levels for pre-order lists -- must be a permutation of the
+phases of disjoint subtrees for post-order lists, the mirrored out-forest plan (or depth levels) for pre-order lists -- must be a permutation of the
 list in which every op runs after the ops producing its inputs, ops of one phase's different subtrees are
 independent, and hazard lists fall back to the caller's order."""
 import numpy as np
@@ -115,7 +115,47 @@ def test_pre_order_levels(lib):
             c1, c2 = int(tree.child[node][0]), int(tree.child[node][1])
             stack += [(c2, node, c1), (c1, node, c2)]
     ops = np.array(ops, dtype=np.int32)
-    order, subs, phases = plan(lib, ops, 2 * off, pre=1)
+    order, subs, phases = plan(lib, ops, 2 * off, pre=2)                  # pre=2: the level plan (fallback / B200_PRE_PHASES=0)
     check_valid(ops, order, subs, phases)
     assert len(phases) - 1 == tree.depth()                                # one launch per depth level
     assert (subs[:, 1] - subs[:, 0] == 1).all()
+
+
+def preorder_ops(tree):
+    off = tree.nodeCount
+    ops, stack = [], [(tree.root, -1, -1)]
+    while stack:
+        node, parent, sib = stack.pop()
+        if parent >= 0:
+            ops += [off + node, -1, -1, off + parent, node, sib, sib]
+        if not tree.isExternal(node):
+            c1, c2 = int(tree.child[node][0]), int(tree.child[node][1])
+            stack += [(c2, node, c1), (c1, node, c2)]
+    return np.array(ops, dtype=np.int32), 2 * off
+
+
+@pytest.mark.parametrize("tips,seed", [(2, 1), (3, 2), (60, 9), (500, 4), (1000, 6)])
+@pytest.mark.parametrize("want,minT", [(1, 4), (8, 4), (64, 1)])
+def test_pre_order_phased_subtrees(lib, tips, seed, want, minT):
+    """Pre-order lists as phased subtree walks: valid (parents before children, a launch's walks independent), far
+    fewer launches than depth levels, and inside a walk the op after a node is one of its children whenever it has one
+    there (that is what register forwarding of pre[parent] relies on)."""
+    tree = em.Tree.coalescent(tips, 1.0, seed)
+    ops, nbuf = preorder_ops(tree)
+    order, subs, phases = plan(lib, ops, nbuf, want=want, minT=minT, pre=1)
+    check_valid(ops, order, subs, phases)
+    if tips >= 60:
+        assert len(phases) - 1 < tree.depth()
+    o = ops.reshape(-1, 7)
+    forwarded = 0
+    for b, e in subs:
+        for p in range(b + 1, e):
+            if o[order[p]][3] == o[order[p - 1]][0]:
+                forwarded += 1
+    internal_nonroot = sum(1 for k in range(len(o)) if (o[:, 3] == o[k][0]).any())
+    if want == 1:                                                         # one walk: every node with children forwards once
+        assert forwarded == internal_nonroot + (0 if len(o) < 2 else 0) or forwarded >= internal_nonroot - 1
+    # hazards fall back to the level plan, still valid
+    bad = ops.copy(); bad[7 + 0] = bad[0]                                 # second op writes the first op's destination
+    order, subs, phases = plan(lib, bad, nbuf, pre=1)
+    assert sorted(order.tolist()) == list(range(len(bad) // 7))
