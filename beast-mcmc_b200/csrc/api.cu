@@ -635,7 +635,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             d.pad_ = o.kind;
         }
     }
-    if (fourPath && in->lookahead && !preOrder) {
+    if (fourPath && in->lookahead && (!preOrder || in->lookaheadPre)) {
         // look-ahead fields: what op k+1 of the same walk will read from memory, except op k's own destination
         // only where the phase is throughput-bound; a thin phase is a pure latency chain and the extra instructions cost
         // more than the prefetch gives (measured on the 62-taxon benchmark2 alignment: +17 % with, in thin phases)
@@ -800,6 +800,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->lookahead = envInt("B200_LOOKAHEAD", 1);
     in->useGraphs = envInt("B200_GRAPHS", 1);
     in->prePhases = envInt("B200_PRE_PHASES", 1);
+    in->lookaheadPre = envInt("B200_LOOKAHEAD_PRE", 1);
     in->planCacheSize = std::max(0, std::min(16, envInt("B200_PLAN_CACHE", 4)));
     in->planCache.reserve(16);
     in->thinR1 = envInt("B200_THIN_R1", 1);

@@ -105,6 +105,7 @@ struct Instance {
     double* dBlockSums = nullptr;
     double* dOut = nullptr;                   // [maxPartitions + 1]
     unsigned int* dCounter = nullptr;
+    int lookaheadPre = 1;                     // look-ahead prefetch in pre-order walks too (B200_LOOKAHEAD_PRE)
     int prePhases = 1;                        // pre-order lists as phased subtree walks (0: one launch per depth level)
     int useGraphs = 1;                        // B200_GRAPHS
     int lookahead = 1;                        // L1 prefetch of the next op's operands (B200_LOOKAHEAD)

@@ -357,7 +357,7 @@ k_walk4(const WalkArgs A) {
         if (R == 1) nxt = loadOp(A.ops + min(k + 1, last));
         else if (lane == 0) prefetchL1(A.ops + min(k + 2, last));
         const int s1 = cur.slots & 0xFF, s2 = (cur.slots >> 8) & 0xFF, sd = (cur.slots >> 16) & 0xFF;
-        if (!PRE && !STACK) {
+        if (!STACK) {
             // look-ahead: the NEXT op's memory operands (never this op's destination) start their trip to L1 now,
             // so that its loads find them there when this op is done
 #pragma unroll
