@@ -461,7 +461,11 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         auto wantSubsFor = [&](int window) {
             const int warpsPerSub = std::max(1, (window + patsPerWarp - 1) / patsPerWarp);
             // enough (subtree x tile) walks to fill every SM, oversubscribed for balance
-            return std::max(1, in->phaseOversub * ((in->smCount * warpsPerSM + warpsPerSub - 1) / warpsPerSub));
+            // oversubscription for balance: 2x where a subtree is only a few warps wide (small alignments), 1x where every
+            // subtree already spreads over dozens of warps -- longer walks forward more results through registers
+            // (measured: cfg 2 +3 %, codon +5 %, benchmark2 +4 %; benchmark1-sized inputs -1..-3 % if forced to 1)
+            const int over = in->phaseOversub > 0 ? in->phaseOversub : (warpsPerSub >= 32 ? 1 : 2);
+            return std::max(1, over * ((in->smCount * warpsPerSM + warpsPerSub - 1) / warpsPerSub));
         };
         if (!byPartition) {
             if (hops[0].kind == 1 && in->prePhases) planPreorderPhases(hops, in->nBuffers, in->phaseT, wantSubsFor(in->Ppad), in->phaseTmin, in->phaseSmall, plan);
@@ -808,7 +812,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->phaseT = envInt("B200_PHASE_T", 0);
     in->phaseTmin = std::max(1, envInt("B200_PHASE_TMIN", 4));
     in->phaseSmall = envInt("B200_PHASE_SMALL", 24);
-    in->phaseOversub = std::max(1, envInt("B200_PHASE_OVERSUB", 2));
+    in->phaseOversub = std::max(0, envInt("B200_PHASE_OVERSUB", 0));      // 0 = by subtree width (see wantSubsFor)
     in->walkMinBlocks = envInt("B200_WALK_MINB", 4);
     in->tensorR = envInt("B200_TENSOR_R", 2) >= 4 ? 4 : 2;
     in->genericMma = envInt("B200_GENERIC_MMA", 1);

@@ -145,7 +145,7 @@ struct Instance {
     int tensorR = 2;             // 8-pattern tiles per warp in the 4-state tensor walk (2 or 4)
     int genericMma = 1;          // S > 4: 1 = fp64 tensor-core block walk, 0 = FMA block walk
     int walkR = 4;               // patterns per thread in the 4-state walk (1, 2 or 4)
-    int phaseTmin = 4, phaseOversub = 2, phaseSmall = 24;   // phaseSmall: a remainder this short runs as one launch
+    int phaseTmin = 4, phaseOversub = 0, phaseSmall = 24;   // phaseSmall: a remainder this short runs as one launch
     int phaseT = 0;              // max ops per subtree walk (0 = automatic)
 };
 
