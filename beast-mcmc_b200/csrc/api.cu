@@ -408,15 +408,17 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             int launches = 0;
             for (size_t ph = 0; ph + 1 < cp.phaseStart.size(); ++ph) launches += cp.phaseStart[ph + 1] > cp.phaseStart[ph];
             if (in->useGraphs && launches >= 2) {
-                if (cp.graphExec == nullptr && cp.hits >= 2 && !in->timing &&
+                if (cp.graphExec == nullptr && !cp.graphFailed && cp.hits >= 2 && !in->timing &&
                     cudaStreamBeginCapture(in->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                     const cudaError_t e1 = launchPlan(in, cp.dBlock, static_cast<char*>(cp.dBlock) + cp.subsOffset, cp.phaseStart,
                                                       cp.phaseDepth, cp.fourPath, cp.maxWindow, cp.preOrder);
                     cudaGraph_t g = nullptr;
                     const cudaError_t e2 = cudaStreamEndCapture(in->stream, &g);
                     if (e1 != cudaSuccess || e2 != cudaSuccess || g == nullptr ||
-                        cudaGraphInstantiate(&cp.graphExec, g, 0) != cudaSuccess)
+                        cudaGraphInstantiate(&cp.graphExec, g, 0) != cudaSuccess) {
                         cp.graphExec = nullptr;
+                        cp.graphFailed = true;
+                    }
                     if (g) cudaGraphDestroy(g);
                     cudaGetLastError();
                 }
@@ -693,6 +695,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         const size_t need = subsOffset + subBytes;
         if (slot->graphExec) { cudaGraphExecDestroy(slot->graphExec); slot->graphExec = nullptr; }
         slot->hits = 0;
+        slot->graphFailed = false;
         if (slot->capacity < need) {
             if (slot->dBlock) cudaFree(slot->dBlock);
             slot->dBlock = nullptr; slot->capacity = 0;

@@ -67,6 +67,7 @@ struct CachedPlan {
     long lastUse = 0;
     long hits = 0;
     cudaGraphExec_t graphExec = nullptr;      // the plan's phase launches as one graph launch (plans with >= 2 launches)
+    bool graphFailed = false;                 // capture or instantiation failed once: plain launches from then on
 };
 
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
