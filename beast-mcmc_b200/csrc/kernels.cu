@@ -222,11 +222,13 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
 // Each thread owns the 4 states of one (pattern, category) cell = 32 contiguous bytes in [C][Ppad][4].
 // Per op and warp the L1/LSU wavefront budget is what bounds this kernel once HBM writes are the only
 // DRAM traffic, so every access is shaped to touch the fewest 128-byte lines:
-//   * op record: 48 B, warp-uniform, three 128-bit loads, fetched ONE OP AHEAD (off the critical path)
+//   * op record: 64 B, warp-uniform, four 128-bit loads; record k+2 is prefetched to L1, record k+1 read after the
+//     arithmetic (R > 1) or one op ahead (R = 1); it also names what the NEXT op will read (look-ahead prefetch)
 //   * matrices : layout [j][CP][i] -> row j of all categories is one 128-byte line, 4 loads per child
-//   * children produced earlier in the same list: per-thread operand stack in shared memory,
+//   * the child produced by the previous op of the walk: taken from the thread's own registers (op flag bit 1);
+//     optional variant (B200_WALK_VARIANT=1): a per-thread operand stack in shared memory for every such child,
 //     laid out [slot][half][thread] so every LDS.128/STS.128 is bank-conflict free
-//   * tip states: one byte per pattern, fetched one op ahead
+//   * tip states: one byte per pattern; their line is prefetched one op ahead
 struct WalkArgs {
     const Op4* ops;
     const int4* subs;          // [subtree] = (first op, one-past-last op, first pattern, one-past-last pattern)

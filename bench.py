@@ -536,7 +536,8 @@ def main():
         "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
         "vs_baseline": None, "logL": joint, "joint_evals_per_s": args.steps / (dev_ms * 1e-3),
         "roofline": {"bound": "hbm", "kernel": "k_walk4 (updatePartials, whole op list per launch)"
-                     if S <= 4 else "k_walk_generic", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     if S <= 4 else "k_walk_mma (updatePartials on the fp64 tensor pipe; math-bound for S=61: see gflops)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      # DRAM-side view of the same launches: measured bytes (ncu) over the live time.  frac counts ALGORITHMIC
                      # bytes, of which children re-read from L2 never reach HBM -- it can exceed 1; dram_frac cannot.
