@@ -243,6 +243,35 @@ class GammaSiteRateModel:
         return self.proportions
 
 
+class GammaSiteModel(GammaSiteRateModel):
+    """The older site model (dr.oldevomodel.sitemodel.GammaSiteModel.java:271-311) that LikelihoodTest.java drives: same
+    median-quantile gamma categories, but the rates are normalised so that the proportion-weighted mean over ALL categories,
+    the invariant one included, is one (mean = pVariable * sum / K), and the +I-only model uses rate 1 / pVariable."""
+
+    def __init__(self, shape=None, gammaCategoryCount=1, pInv=None, mu=1.0):
+        from scipy.stats import gamma as _gamma
+        if shape is None:
+            gammaCategoryCount = 1
+        cat = 1 if pInv is not None else 0
+        n = gammaCategoryCount + cat
+        rates, props = np.zeros(n), np.zeros(n)
+        pVar = 1.0
+        if pInv is not None:
+            props[0] = pInv
+            pVar = 1.0 - pInv
+        if shape is not None:
+            k = gammaCategoryCount
+            for i in range(k):
+                rates[i + cat] = _gamma.ppf((2.0 * i + 1.0) / (2.0 * k), a=shape, scale=1.0 / shape)
+                props[i + cat] = pVar / k
+            rates[cat:] /= (pVar * rates[cat:].sum()) / k
+        else:
+            rates[cat] = 1.0 / pVar
+            props[cat] = pVar
+        self.rates = rates * mu
+        self.proportions = props
+
+
 # ----------------------------------------------------------------------------------------------
 # trees
 # ----------------------------------------------------------------------------------------------

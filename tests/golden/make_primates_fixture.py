@@ -5,6 +5,8 @@ Extracts the reference's own golden INPUTS for the hot path into tests/golden/pr
   * the 6-primate x 768-nt alignment   src/test/dr/inference/trace/TraceCorrelationAssert.java:192-198
   * the fixed-height primate tree       TraceCorrelationAssert.java:145-190
   * the ten expected log-likelihoods    src/test/dr/evomodel/treedatalikelihood/TreeDataLikelihoodTest.java:131-314
+  * ten more, with their parameters      src/test/dr/evomodel/treelikelihood/LikelihoodTest.java:86-341 (older TreeLikelihood,
+                                         dr.oldevomodel.sitemodel.GammaSiteModel rate rule)
   * the BEAGLE tiny test (3 taxa, JC69) src/test/dr/app/beagle/TinyTest.java:101-107 + lib/beagle.jar BeagleFactory.main
 """
 import json, re, sys
@@ -26,6 +28,21 @@ def main():
     test = open(f"{REF}/src/test/dr/evomodel/treedatalikelihood/TreeDataLikelihoodTest.java").read()
     expected = dict(re.findall(r'assertEquals\("treeLikelihood(\w+)", format.format\((-[\d.]+)\)', test))
     heights = re.findall(r"setHeight\((\d+\.\d+)\)", open(tca).read())[:5]
+    # the same data through the older pure-Java TreeLikelihood: ten more pinned values with their own parameters
+    lt = open(f"{REF}/src/test/dr/evomodel/treelikelihood/LikelihoodTest.java").read()
+    legacy = {}
+    for body in re.split(r"public void testLikelihood", lt)[1:]:
+        name = re.match(r"(\w+)\(\)", body).group(1)
+        val = re.search(r'assertEquals\("treeLikelihood\w+", format.format\((-[\d.]+)\)', body)
+        if not val:
+            continue
+        par = lambda key: (lambda m: float(m.group(1)) if m else None)(re.search(key + r",\s*([\d.]+),", body))
+        legacy[name] = {"logL": float(val.group(1)), "kappa": par(r"HKYParser\.KAPPA"),
+                        "shape": par(r"GammaSiteModelParser\.GAMMA_SHAPE"),
+                        "pInv": par(r"GammaSiteModelParser\.PROPORTION_INVARIANT"),
+                        "empiricalFrequencies": "alignment.getStateFrequencies()" in body,
+                        "model": "GTR" if "new GTR(" in body else "HKY"}
+    assert len(legacy) == 10, legacy.keys()
     out = {
         "primates": {
             "taxa": ["human", "chimp", "bonobo", "gorilla", "orangutan", "siamang"],
@@ -34,6 +51,7 @@ def main():
                                  "plus_gorilla": float(heights[2]), "plus_orangutan": float(heights[3]),
                                  "root": float(heights[4])}},
             "expected_logL": {k: float(v) for k, v in expected.items()},
+            "legacy_likelihood_test": legacy,
         },
         "tiny": {
             "taxa": ["human", "chimp", "gorilla"],

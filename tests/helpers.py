@@ -69,6 +69,22 @@ def primate_cases():
     }
 
 
+def primate_cases_legacy():
+    """name -> (substitution model, site model, expected logL): the ten cases of LikelihoodTest.java:86-341 -- the same
+    alignment and tree through the older TreeLikelihood, with that test's own parameters and the older site-model rate
+    rule (dr.oldevomodel.sitemodel.GammaSiteModel.java:271-311)."""
+    pats = primate_patterns()
+    emp = pats.stateFrequencies()
+    uni = np.full(4, 0.25)
+    out = {}
+    for name, c in GOLDEN["primates"]["legacy_likelihood_test"].items():
+        freqs = emp if c["empiricalFrequencies"] else uni
+        model = em.GTR(1.0, 1.0, 1.0, 1.0, 1.0, 1.0, freqs) if c["model"] == "GTR" else em.HKY(c["kappa"], freqs)
+        site = em.GammaSiteModel(shape=c["shape"], gammaCategoryCount=4 if c["shape"] is not None else 1, pInv=c["pInv"])
+        out[name] = (model, site, c["logL"])
+    return out
+
+
 def tiny_case():
     g = GOLDEN["tiny"]
     pats = em.Patterns.fromAlignment(em.encode_nucleotides(g["sequences"]), unique=False)

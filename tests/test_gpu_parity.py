@@ -49,6 +49,18 @@ def test_primates_golden(name):
     d.finalize()
 
 
+@pytest.mark.parametrize("name", list(H.primate_cases_legacy().keys()))
+def test_primates_golden_legacy_likelihood_test(name):
+    """The ten values of LikelihoodTest.java:106-341 (other parameters, the older site-model rate rule), alternately with
+    and without rescaling."""
+    model, site, expected = H.primate_cases_legacy()[name]
+    scheme = S_.ALWAYS if len(name) % 2 else S_.NONE
+    d = _delegate(H.primate_tree(), H.primate_patterns(), model, site, GPU, rescalingScheme=scheme,
+                  delayRescalingUntilUnderflow=False)
+    assert _fmt(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood()) == _fmt(expected)
+    d.finalize()
+
+
 def test_tiny_test_golden():
     tree, pats, model, site, expected = H.tiny_case()
     d = _delegate(tree, pats, model, site, GPU, rescalingScheme=S_.NONE)

@@ -1,5 +1,6 @@
 """Pin the oracle (and the caller re-enactment) to the reference's own golden vectors:
-TreeDataLikelihoodTest.java:131-314 (ten values, 5 decimals) and the BEAGLE tiny test."""
+TreeDataLikelihoodTest.java:131-314 (ten values, 5 decimals), LikelihoodTest.java:106-341 (ten more, other parameters,
+the older site-model rate rule) and the BEAGLE tiny test."""
 import numpy as np
 import pytest
 
@@ -24,6 +25,15 @@ def test_primates_through_delegate(name, traversal_flags):
     assert _fmt(like.getLogLikelihood()) == _fmt(expected)
     # the DYNAMIC scheme with delay=false rescales on the very first evaluation
     assert delegate.useScaleFactors
+
+
+@pytest.mark.parametrize("name", list(H.primate_cases_legacy().keys()))
+def test_primates_legacy_likelihood_test_values(name):
+    """LikelihoodTest.java:106-341: K80 kappa=27.402591, HKY85+G kappa=38.829740 alpha=0.137064, HKY85+I pInv=0.701211, ..."""
+    model, site, expected = H.primate_cases_legacy()[name]
+    d = tdl.BeagleDataLikelihoodDelegate(H.primate_tree(), H.primate_patterns(), model, site, H.oracle_factory(),
+                                         rescalingScheme=tdl.PartialsRescalingScheme.NONE)
+    assert _fmt(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood()) == _fmt(expected)
 
 
 def test_primates_unscaled_equals_scaled():
@@ -75,6 +85,15 @@ def cport():
 def test_c_port_primates_golden(cport, name):
     model, site, expected = H.primate_cases()[name]
     d = tdl.BeagleDataLikelihoodDelegate(H.primate_tree(), H.primate_patterns(), model, site, cport.factory(threads=3),
+                                         delayRescalingUntilUnderflow=False)
+    assert _fmt(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood()) == _fmt(expected)
+    d.finalize()
+
+
+@pytest.mark.parametrize("name", list(H.primate_cases_legacy().keys()))
+def test_c_port_primates_legacy_golden(cport, name):
+    model, site, expected = H.primate_cases_legacy()[name]
+    d = tdl.BeagleDataLikelihoodDelegate(H.primate_tree(), H.primate_patterns(), model, site, cport.factory(threads=2),
                                          delayRescalingUntilUnderflow=False)
     assert _fmt(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood()) == _fmt(expected)
     d.finalize()
