@@ -85,6 +85,63 @@ def primate_cases_legacy():
     return out
 
 
+def _newick_to_tree(newick):
+    """Ultrametric newick with branch lengths -> (em.Tree, tip names in taxonN order); heights from the lengths."""
+    import re
+    tokens = re.findall(r"[(),;]|[^(),;:]+|:[0-9.eE+-]+", newick.strip())
+    pos = [0]
+
+    def node():
+        if tokens[pos[0]] == "(":
+            pos[0] += 1
+            kids = [node()]
+            while tokens[pos[0]] == ",":
+                pos[0] += 1
+                kids.append(node())
+            assert tokens[pos[0]] == ")" and len(kids) == 2
+            pos[0] += 1
+            name = None
+        else:
+            kids, name = None, tokens[pos[0]]
+            pos[0] += 1
+        length = 0.0
+        if pos[0] < len(tokens) and tokens[pos[0]].startswith(":"):
+            length = float(tokens[pos[0]][1:])
+            pos[0] += 1
+        return (name, kids, length)
+
+    root = node()
+    names = sorted(re.findall(r"taxon\d+", newick), key=lambda t: int(t[5:]))
+
+    def build(n):
+        name, kids, _ = n
+        if kids is None:
+            return name, 0.0
+        (a, ha), (b, hb) = build(kids[0]), build(kids[1])
+        h1, h2 = ha + kids[0][2], hb + kids[1][2]
+        assert abs(h1 - h2) < 1e-12, "fixture trees are ultrametric"
+        return (a, b, h1), h1
+
+    spec, _ = build(root)
+    return em.Tree.fromNested(spec, names), names
+
+
+def msat_cases():
+    """[(tree, patterns, model, site model, expected logL)]: MsatFullLikelihoodTest.java:60-190, pinned there to 1e-10.
+    Default AsymmetricQuadraticModel = stepwise mutation model (rate 1 to either neighbour state), normalised to one expected
+    substitution, uniform stationary root frequencies."""
+    import json
+    out = []
+    for c in json.load(open(os.path.join(ROOT, "tests", "golden", "msat.json")))["cases"]:
+        S = c["stateCount"]
+        tree, names = _newick_to_tree(c["newick"])
+        rates = [1.0 if j == i + 1 else 0.0 for i in range(S) for j in range(i + 1, S)]
+        model = em.SubstitutionModel(rates, np.full(S, 1.0 / S))
+        pats = em.Patterns(np.asarray(c["pattern"], dtype=np.int32)[:, None], np.ones(1), S)
+        out.append((tree, pats, model, em.GammaSiteRateModel(), c["logL"]))
+    return out
+
+
 def tiny_case():
     g = GOLDEN["tiny"]
     pats = em.Patterns.fromAlignment(em.encode_nucleotides(g["sequences"]), unique=False)

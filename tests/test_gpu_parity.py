@@ -61,6 +61,17 @@ def test_primates_golden_legacy_likelihood_test(name):
     d.finalize()
 
 
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_msat_hand_calculated_values_to_1e10(k):
+    """MsatFullLikelihoodTest.java:181-189 through the C ABI: 3 states on the 4-state kernel (S < 4), 4 states, one pattern;
+    the reference asserts 1e-10."""
+    tree, pats, model, site, expected = H.msat_cases()[k]
+    for scheme in (S_.NONE, S_.ALWAYS):
+        d = _delegate(tree, pats, model, site, GPU, rescalingScheme=scheme, delayRescalingUntilUnderflow=False)
+        assert abs(tdl.TreeDataLikelihood(d, tree).getLogLikelihood() - expected) <= 1e-10
+        d.finalize()
+
+
 def test_tiny_test_golden():
     tree, pats, model, site, expected = H.tiny_case()
     d = _delegate(tree, pats, model, site, GPU, rescalingScheme=S_.NONE)

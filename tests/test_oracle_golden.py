@@ -36,6 +36,16 @@ def test_primates_legacy_likelihood_test_values(name):
     assert _fmt(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood()) == _fmt(expected)
 
 
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_msat_hand_calculated_values_to_1e10(k):
+    """MsatFullLikelihoodTest.java:181-189: the only values the reference pins to 1e-10 (3- and 4-state stepwise models)."""
+    tree, pats, model, site, expected = H.msat_cases()[k]
+    for scheme in (tdl.PartialsRescalingScheme.NONE, tdl.PartialsRescalingScheme.ALWAYS):
+        d = tdl.BeagleDataLikelihoodDelegate(tree, pats, model, site, H.oracle_factory(), rescalingScheme=scheme,
+                                             delayRescalingUntilUnderflow=False)
+        assert abs(tdl.TreeDataLikelihood(d, tree).getLogLikelihood() - expected) <= 1e-10
+
+
 def test_primates_unscaled_equals_scaled():
     model, site, expected = H.primate_cases()["GTRGI"]
     vals = []
@@ -96,6 +106,14 @@ def test_c_port_primates_legacy_golden(cport, name):
     d = tdl.BeagleDataLikelihoodDelegate(H.primate_tree(), H.primate_patterns(), model, site, cport.factory(threads=2),
                                          delayRescalingUntilUnderflow=False)
     assert _fmt(tdl.TreeDataLikelihood(d, H.primate_tree()).getLogLikelihood()) == _fmt(expected)
+    d.finalize()
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_c_port_msat_hand_calculated_values(cport, k):
+    tree, pats, model, site, expected = H.msat_cases()[k]
+    d = tdl.BeagleDataLikelihoodDelegate(tree, pats, model, site, cport.factory(threads=1))
+    assert abs(tdl.TreeDataLikelihood(d, tree).getLogLikelihood() - expected) <= 1e-10
     d.finalize()
 
 
