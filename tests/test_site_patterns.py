@@ -38,6 +38,33 @@ def test_numpy_mirror_equals_java_loop():
     assert np.array_equal(pats[:, idx], states)
 
 
+def primate_alignment():
+    return em.encode_nucleotides(H.GOLDEN["primates"]["sequences"]).astype(np.int32)
+
+
+def test_reference_pattern_counts_on_the_primate_alignment():
+    """SitePatternsTest.java:75-99: 768 sites, 69 unique patterns, 37 unique patterns among the third codon positions
+    (from = 2, every = 3)."""
+    aln = primate_alignment()
+    assert aln.shape == (6, 768)
+    for cols, expected in ((aln, 69), (aln[:, 2::3], 37)):
+        pats, w, idx = java_add_patterns(np.ascontiguousarray(cols))
+        m = em.Patterns.fromAlignment(cols)
+        assert pats.shape[1] == expected == m.patternCount and w.sum() == cols.shape[1]
+        assert np.array_equal(m.states, pats) and np.array_equal(m.weights, w)
+
+
+@pytest.mark.gpu
+def test_gpu_reference_pattern_counts_on_the_primate_alignment():
+    from beast_mcmc_b200 import beagle
+    aln = primate_alignment()
+    for cols, expected in ((aln, 69), (np.ascontiguousarray(aln[:, 2::3]), 37)):
+        pats, w, idx = beagle.compressSitePatterns(cols)
+        epats, ew, eidx = java_add_patterns(cols)
+        assert pats.shape[1] == expected
+        assert np.array_equal(pats, epats) and np.array_equal(w, ew) and np.array_equal(idx, eidx)
+
+
 CASES = [(5, 400, 3, 1), (1, 50, 2, 2), (40, 3000, 4, 3), (7, 1, 4, 4), (3, 2000, 18, 5), (300, 700, 2, 6)]
 
 
