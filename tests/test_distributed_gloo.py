@@ -43,3 +43,21 @@ def test_two_rank_pattern_sharding(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "OK" in o, o
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches `bench.py --impl reference --gpus N` the same way as the GPU arm (torchrun, N ranks): rank 0 alone
+    times the CPU restatement and prints the JSON line, the other ranks exit 0 without work.  No GPU involved."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--workload", "hky_1441x593", "--steps", "2", "--warmup", "3"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["metric"] == "tree log-likelihood evals/sec" and d["config"]["workload"] == "hky_1441x593"
