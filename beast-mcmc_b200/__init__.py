@@ -6,8 +6,9 @@ The directory name carries a hyphen (as the project is named); import it as
 
   csrc/                  CUDA kernels, the C ABI (include/libhmsbeagle_b200.h) and the JNI shim
   beagle.py              ctypes mirror of the ``beagle.Beagle`` Java interface over the C ABI
-  treedatalikelihood.py  re-enactment of BeagleDataLikelihoodDelegate / TreeDataLikelihood
-  evomodel.py            producers of the inputs BEAST hands to BEAGLE (eigen systems, rates, trees)
   build.py               in-tree nvcc build of the shared libraries
+
+The Python re-enactments of the reference's Java callers (test/bench harness) live in ``harness/`` at the repo root,
+not here: the product is the two shared libraries under csrc/.
 """
-__all__ = ["beagle", "treedatalikelihood", "evomodel", "build"]
+__all__ = ["beagle", "build"]

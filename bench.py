@@ -36,8 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import beast_mcmc_b200  # noqa: E402,F401
-from beast_mcmc_b200 import evomodel as em  # noqa: E402
-from beast_mcmc_b200 import treedatalikelihood as tdl  # noqa: E402
+from harness import evomodel as em  # noqa: E402
+from harness import treedatalikelihood as tdl  # noqa: E402
 
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1

@@ -14,7 +14,7 @@ import numpy as np
 
 sys.path.insert(0, __file__.rsplit("/tests/", 1)[0])
 import beast_mcmc_b200  # noqa
-from beast_mcmc_b200 import evomodel as em
+from harness import evomodel as em
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 HERE = __file__.rsplit("/", 1)[0]

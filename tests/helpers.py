@@ -11,8 +11,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 import beast_mcmc_b200  # noqa: E402
-from beast_mcmc_b200 import evomodel as em  # noqa: E402
-from beast_mcmc_b200 import treedatalikelihood as tdl  # noqa: E402
+from harness import evomodel as em  # noqa: E402
+from harness import treedatalikelihood as tdl  # noqa: E402
 from oracle.felsenstein import OracleBeagle  # noqa: E402
 
 GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "primates.json")))

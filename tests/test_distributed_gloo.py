@@ -13,7 +13,8 @@ WORKER = textwrap.dedent("""
     sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
     import torch.distributed as dist
     import helpers as H
-    from beast_mcmc_b200 import sharding, treedatalikelihood as tdl, build
+    from beast_mcmc_b200 import build
+    from harness import sharding, treedatalikelihood as tdl
     from oracle import cpu
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)

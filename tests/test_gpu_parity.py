@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 import helpers as H
-from beast_mcmc_b200 import beagle, evomodel as em, treedatalikelihood as tdl
+from beast_mcmc_b200 import beagle
+from harness import evomodel as em, treedatalikelihood as tdl
 
 pytestmark = pytest.mark.gpu
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from beast_mcmc_b200 import treedatalikelihood as tdl
+from harness import treedatalikelihood as tdl
 
 
 def _fmt(x):
@@ -61,7 +61,7 @@ def test_primates_unscaled_equals_scaled():
 
 
 def test_primates_ambiguities_as_partials():
-    from beast_mcmc_b200.evomodel import nucleotide_state_set
+    from harness.evomodel import nucleotide_state_set
     model, site, expected = H.primate_cases()["HKY85G"]
     d = tdl.BeagleDataLikelihoodDelegate(H.primate_tree(), H.primate_patterns(), model, site, H.oracle_factory(),
                                          useAmbiguities=True, stateSetFn=nucleotide_state_set)

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 import helpers as H
-from beast_mcmc_b200 import beagle, build, evomodel as em, treedatalikelihood as tdl
+from beast_mcmc_b200 import beagle, build
+from harness import evomodel as em, treedatalikelihood as tdl
 
 
 @pytest.fixture(scope="module")

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from beast_mcmc_b200 import treedatalikelihood as tdl
+from harness import treedatalikelihood as tdl
 
 
 def gradient_and_fd(factory, tree, pats, model, site, resourceList=None, eps=1e-6, nodes=None):

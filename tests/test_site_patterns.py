@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from beast_mcmc_b200 import evomodel as em
+from harness import evomodel as em
 
 
 def java_add_patterns(states, siteWeights=None):

@@ -9,7 +9,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import beast_mcmc_b200  # noqa
-from beast_mcmc_b200 import beagle, evomodel as em, treedatalikelihood as tdl
+from beast_mcmc_b200 import beagle
+from harness import evomodel as em, treedatalikelihood as tdl
 
 import bench
 

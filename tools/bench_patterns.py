@@ -7,7 +7,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import beast_mcmc_b200  # noqa
-from beast_mcmc_b200 import beagle, evomodel as em
+from beast_mcmc_b200 import beagle
+from harness import evomodel as em
 
 TAXA, SITES = int(os.environ.get("TAXA", 1610)), int(os.environ.get("SITES", 18992))
 tree = em.Tree.coalescent(TAXA, 0.0025, 3)
