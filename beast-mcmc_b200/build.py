@@ -4,10 +4,15 @@
   beast-mcmc_b200/csrc/libhmsbeagle-jni.so  the JNI shim BEAST's lib/beagle.jar binds (System.loadLibrary("hmsbeagle-jni"))
   oracle/liboracle_cpu.so                   the CPU restatement used as checker / cpu_baseline (test infrastructure)
 
-The .so files are git-ignored but travel to the GPU box with the gpurun snapshot.
+The .so files are git-ignored but travel to the GPU box with the gpurun snapshot.  So that a travelling binary can never
+silently drift from the sources, a SHA-256 over the engine's sources is compiled into the library (``b200GetSourceHash``,
+also the build-metadata suffix of ``beagleGetVersion``) and written next to it; ``build_engine`` rebuilds whenever the
+recorded hash differs from the sources' and ``verify_engine`` asserts the LOADED library reports the current hash.
 """
 from __future__ import annotations
 
+import concurrent.futures
+import hashlib
 import os
 import shutil
 import subprocess
@@ -18,6 +23,20 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+ENGINE_UNITS = ("api.cu", "kernels.cu", "walk4e.cu", "multi.cu", "patterns.cu")
+ENGINE_HEADERS = (os.path.join(CSRC, "engine.h"), os.path.join(ROOT, "include", "libhmsbeagle_b200.h"))
+
+
+def _engine_units():
+    return [os.path.join(CSRC, f) for f in ENGINE_UNITS if os.path.exists(os.path.join(CSRC, f))]
+
+
+def source_hash() -> str:
+    h = hashlib.sha256()
+    for path in sorted(_engine_units()) + sorted(ENGINE_HEADERS):
+        h.update(os.path.basename(path).encode() + b"\0")
+        h.update(open(path, "rb").read())
+    return h.hexdigest()[:16]
 
 
 def _stale(target, sources):
@@ -43,14 +62,44 @@ def lib_path(name="libhmsbeagle.so"):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "kernels.cu", "patterns.cu")]
-    deps = srcs + [os.path.join(CSRC, "engine.h"), os.path.join(ROOT, "include", "libhmsbeagle_b200.h")]
     out = lib_path()
-    if force or _stale(out, deps):
-        _run([NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-              "-shared", "-cudart", "static", "-Xptxas", "-v" if verbose else "-O3",
-              "-o", out, *srcs], verbose)
+    stamp = out + ".srchash"
+    want = source_hash()
+    have = open(stamp).read().strip() if os.path.exists(stamp) and os.path.exists(out) else None
+    if not force and have == want:
+        return out
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"{out} is stale (sources {want}, binary {have}) and nvcc is not available to rebuild it")
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    common = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+              "-Xptxas", "-v" if verbose else "-O3"]
+
+    def compile_unit(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        extra = [f'-DB200_SOURCE_HASH="{want}"'] if src.endswith("api.cu") else []
+        # api.cu carries the hash of ALL sources: it is recompiled whenever anything changed
+        if force or extra or _stale(obj, [src, *ENGINE_HEADERS]):
+            _run([*common, *extra, "-c", "-o", obj, src], verbose)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_unit, _engine_units()))
+    _run([NVCC, *ARCH, "-shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-o", out, *objs, "-lpthread"], verbose)
+    with open(stamp, "w") as f:
+        f.write(want + "\n")
     return out
+
+
+def verify_engine():
+    """The library that actually loads must have been built from the sources in this tree."""
+    import ctypes
+    lib = ctypes.CDLL(lib_path())
+    lib.b200GetSourceHash.restype = ctypes.c_char_p
+    got, want = lib.b200GetSourceHash().decode(), source_hash()
+    if got != want:
+        raise RuntimeError(f"libhmsbeagle.so was built from other sources (binary {got}, tree {want}): rebuild")
+    return got
 
 
 def build_jni(force=False, verbose=False):
@@ -71,8 +120,8 @@ def build_oracle(force=False, verbose=False):
         return None
     out = os.path.join(ROOT, "oracle", "liboracle_cpu.so")
     if force or _stale(out, [src]):
-        _run(["gcc", "-O3", "-march=native", "-std=gnu11", "-fPIC", "-shared", "-pthread", "-o", out, src, "-lm"],
-             verbose)
+        # no -march=native: the binary travels to a different host CPU; the hot loops carry target_clones instead
+        _run(["gcc", "-O3", "-std=gnu11", "-fPIC", "-shared", "-pthread", "-o", out, src, "-lm"], verbose)
     return out
 
 
@@ -81,4 +130,5 @@ def build_all(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_all(force="--force" in sys.argv, verbose=True))
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print("source hash", verify_engine())

@@ -130,7 +130,7 @@ void destroyInstance(Instance* in) {
     if (in->stream) cudaStreamSynchronize(in->stream);
     cudaFree(in->partialsBase); cudaFree(in->states8Base); cudaFree(in->states32Base);
     for (CachedPlan& cp : in->planCache) { if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec); cudaFree(cp.dBlock); }
-    cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dRates); cudaFree(in->dWeights);
+    cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dEvec); cudaFree(in->dRates); cudaFree(in->dWeights);
     cudaFree(in->dFreqs); cudaFree(in->dScale); cudaFree(in->dPatternWeights);
     cudaFree(in->dPatternPartitions); cudaFree(in->dSite); cudaFree(in->dBlockSums); cudaFree(in->dOut);
     cudaFree(in->dCounter); cudaFree(in->dStage); cudaFree(in->dScratch);
@@ -375,19 +375,57 @@ void planPreorderPhases(const std::vector<HostOp>& ops, int nBuffers, int fixedT
 }
 
 // launch the phases of a prepared plan (device-resident op records + subtree table)
+// eigenSlot >= 0: the 4-state list runs in eigen form (walk4e.cu) with that slot's V / V^-1; aligned: no pattern windows
 cudaError_t launchPlan(Instance* in, const void* dOps, const void* dSubs, const std::vector<int>& phaseStart,
-                       const std::vector<int>& phaseDepth, bool fourPath, int maxWindow, bool preOrder) {
+                       const std::vector<int>& phaseDepth, bool fourPath, int maxWindow, bool preOrder, int eigenSlot = -1,
+                       bool aligned = false) {
     cudaError_t e = cudaSuccess;
     for (size_t ph = 0; ph + 1 < phaseStart.size() && e == cudaSuccess; ++ph) {
         const int s0 = phaseStart[ph], s1 = phaseStart[ph + 1];
         if (s1 <= s0) continue;
         TimedScope ts(in, T_PARTIALS);
+        if (fourPath && eigenSlot >= 0 && !preOrder && (ph >= phaseDepth.size() || phaseDepth[ph] == 0)) {
+            e = launchWalk4E(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0, maxWindow,
+                             aligned, in->hEigen.data() + (size_t)eigenSlot * 36);
+            continue;
+        }
         e = fourPath ? launchWalk4(in, static_cast<const Op4*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0,
                                    ph < phaseDepth.size() ? phaseDepth[ph] : 0, maxWindow, preOrder)
                      : launchWalkGeneric(in, static_cast<const DevOp*>(dOps), static_cast<const int4*>(dSubs) + s0, s1 - s0,
                                          maxWindow, preOrder);
     }
     return e;
+}
+
+// cum[p] += sum_k log factor_k[p] for the in-list cumulative groups of a plan (after its phases, same stream)
+cudaError_t accumulateInList(Instance* in, const std::vector<CumGroup>& groups) {
+    for (const CumGroup& g : groups) {
+        int* dIdx = static_cast<int*>(stage(in, g.indices.data(), sizeof(int) * g.indices.size()));
+        if (dIdx == nullptr) return cudaErrorMemoryAllocation;
+        cudaError_t e = launchScaleAccumulate(in, dIdx, (int)g.indices.size(), in->dScale + (size_t)g.cum * in->Ppad, 1.0,
+                                              g.pBegin, g.pEnd);
+        if (e != cudaSuccess) return e;
+        in->scaleIsLog[g.cum] = 1;
+    }
+    return cudaSuccess;
+}
+
+// per-node scale buffers written by a list hold raw factors (logs under SCALERS_LOG)
+void noteScaleWrites(Instance* in, const std::vector<HostOp>& hops) {
+    for (const HostOp& o : hops) if (o.sw >= 0) in->scaleIsLog[o.sw] = in->logScalers ? 1 : 0;
+}
+
+// The eigen-form walk serves a post-order 4-state list when every matrix it names was computed by
+// updateTransitionMatrices from the CURRENT content of ONE real eigen slot; returns that slot or -1.
+int eigenFormSlot(const Instance* in, const std::vector<HostOp>& hops) {
+    if (!in->eigenWalk || in->matCP == 0 || in->walkVariant != 0 || hops.empty() || hops[0].kind == 1) return -1;
+    const int E = in->matEigen[hops[0].m1];
+    if (E < 0 || !in->eigenReal[E]) return -1;
+    const unsigned gen = in->eigenGen[E];
+    for (const HostOp& o : hops)
+        if (in->matEigen[o.m1] != E || in->matEigen[o.m2] != E || in->matEigenGen[o.m1] != gen || in->matEigenGen[o.m2] != gen)
+            return -1;
+    return E;
 }
 
 int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartition) {
@@ -403,6 +441,15 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
                 continue;
             cp.lastUse = ++in->planClock;
             cp.hits++;
+            const int eigenSlot = cp.fourPath ? eigenFormSlot(in, hops) : -1;
+            const unsigned eigenGenNow = eigenSlot >= 0 ? in->eigenGen[eigenSlot] : 0u;
+            // a captured graph carries the kernel choice and V / V^-1 by value: stale once the eigen system moved on
+            if (cp.graphExec != nullptr && (cp.graphEigen != eigenSlot || cp.graphEigenGen != eigenGenNow)) {
+                cudaGraphExecDestroy(cp.graphExec);
+                cp.graphExec = nullptr;
+                cp.hits = 1;
+                if (++cp.graphInvalidations >= 4) cp.graphFailed = true;     // a model that moves every step: plain launches
+            }
             // A plan that keeps coming back and needs several dependent launches is replayed as ONE graph launch:
             // on small alignments the host-side launch cost, not the kernels, sets the pace.
             int launches = 0;
@@ -411,7 +458,10 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
                 if (cp.graphExec == nullptr && !cp.graphFailed && cp.hits >= 2 && !in->timing &&
                     cudaStreamBeginCapture(in->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                     const cudaError_t e1 = launchPlan(in, cp.dBlock, static_cast<char*>(cp.dBlock) + cp.subsOffset, cp.phaseStart,
-                                                      cp.phaseDepth, cp.fourPath, cp.maxWindow, cp.preOrder);
+                                                      cp.phaseDepth, cp.fourPath, cp.maxWindow, cp.preOrder, eigenSlot,
+                                                      !cp.byPartition);
+                    cp.graphEigen = eigenSlot;
+                    cp.graphEigenGen = eigenGenNow;
                     cudaGraph_t g = nullptr;
                     const cudaError_t e2 = cudaStreamEndCapture(in->stream, &g);
                     if (e1 != cudaSuccess || e2 != cudaSuccess || g == nullptr ||
@@ -425,15 +475,18 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
                 if (cp.graphExec != nullptr) {
                     TimedScope ts(in, T_PARTIALS, launches);
                     CUDA_OK(cudaGraphLaunch(cp.graphExec, in->stream));
+                    noteScaleWrites(in, hops);
                     return BEAGLE_SUCCESS;
                 }
             }
             CUDA_OK(launchPlan(in, cp.dBlock, static_cast<char*>(cp.dBlock) + cp.subsOffset, cp.phaseStart, cp.phaseDepth,
-                               cp.fourPath, cp.maxWindow, cp.preOrder));
+                               cp.fourPath, cp.maxWindow, cp.preOrder, eigenSlot, !cp.byPartition));
+            CUDA_OK(accumulateInList(in, cp.cumGroups));
+            noteScaleWrites(in, hops);
             return BEAGLE_SUCCESS;
         }
     }
-    // ---- validation + lazy allocation
+    // ---- validation (no side effects), then lazy allocation / kind changes
     for (const HostOp& o : hops) {
         if (!validRange(o.dest, in->nBuffers) || !validRange(o.c1, in->nBuffers) ||
             !validRange(o.c2, in->nBuffers) || !validRange(o.m1, in->nMatrices) ||
@@ -443,15 +496,23 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         if (o.sr != BEAGLE_OP_NONE && !validRange(o.sr, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
         if (o.cum != BEAGLE_OP_NONE && !validRange(o.cum, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
         if (byPartition && !validRange(o.part, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    }
+    {
+        // a child must hold data: compact states, partials, or the destination of an op of this very list
+        std::vector<char> written(in->nBuffers, 0);
+        for (const HostOp& o : hops) written[o.dest] = 1;
+        auto holdsData = [&](int b) { return written[b] || in->partials[b] != nullptr || in->states32[b] != nullptr; };
+        for (const HostOp& o : hops) {
+            if (!holdsData(o.c1) || !holdsData(o.c2)) return BEAGLE_ERROR_OUT_OF_RANGE;
+            // pre-order: c1 is pre[parent], a partials buffer by construction
+            if (o.kind == 1 && !written[o.c1] && in->states32[o.c1] != nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+        }
+    }
+    for (const HostOp& o : hops) {
         if (ensurePartials(in, o.dest) == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
         if (in->states32[o.dest] != nullptr) in->bufferEpoch++;
         in->states8[o.dest] = nullptr;      // a written buffer holds partials from now on
         in->states32[o.dest] = nullptr;
-    }
-    for (const HostOp& o : hops) {
-        if (o.kind == 1 && (in->partials[o.c1] == nullptr || in->states32[o.c1] != nullptr)) return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (in->partials[o.c1] == nullptr && in->states32[o.c1] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (in->partials[o.c2] == nullptr && in->states32[o.c2] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
     }
     const bool fourState = in->matCP > 0;
     Plan plan;
@@ -568,6 +629,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
     int depthUsed = 0, depthThisSub = 0, curSub = -1;
 
     const bool fourPath = in->matCP > 0;
+    std::vector<CumGroup> cumGroups;
     std::vector<DevOp> dops(fourPath ? 0 : n);
     std::vector<Op4> ops4(fourPath ? n : 0);
     for (int pos = 0; pos < n; ++pos) {
@@ -603,7 +665,16 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         }
         const int pBegin = byPartition ? in->partBegin[o.part] : 0;
         const int pEnd = byPartition ? in->partEnd[o.part] : in->P;
-        const int cum = (o.cum >= 0 && o.sw >= 0) ? o.cum : -1;
+        // In-list cumulative scaling (cumulativeScaleIndex != NONE) is NOT done inside the walk: independent subtrees of a
+        // phase run concurrently over the same pattern columns, so a "cum[p] += log m" there would race.  The walk only
+        // writes the per-node factors; one k_scale_accum launch per (cumulative buffer, pattern window) follows the phases.
+        if (o.cum >= 0 && o.sw >= 0) {
+            CumGroup* grp = nullptr;
+            for (CumGroup& g : cumGroups) if (g.cum == o.cum && g.pBegin == pBegin && g.pEnd == pEnd) { grp = &g; break; }
+            if (grp == nullptr) { cumGroups.push_back(CumGroup{o.cum, pBegin, pEnd, {}}); grp = &cumGroups.back(); }
+            grp->indices.push_back(o.sw);
+        }
+        const int cum = -1;
         if (fourPath) {
             Op4& d = ops4[pos];
             d.dest = in->slotOf[o.dest];
@@ -679,23 +750,31 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         CUDA_OK(cudaMalloc(&tmp, opBytes + 256 + subBytes));
         dOps = tmp;
         dSubs = static_cast<char*>(tmp) + ((opBytes + 255) & ~size_t(255));
-        CUDA_OK(cudaMemcpyAsync(dOps, hostOps, opBytes, cudaMemcpyHostToDevice, in->stream));
-        CUDA_OK(cudaMemcpyAsync(dSubs, plan.subs.data(), subBytes, cudaMemcpyHostToDevice, in->stream));
-        CUDA_OK(cudaStreamSynchronize(in->stream));
+        cudaError_t ce = cudaMemcpyAsync(dOps, hostOps, opBytes, cudaMemcpyHostToDevice, in->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dSubs, plan.subs.data(), subBytes, cudaMemcpyHostToDevice, in->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(in->stream);
+        if (ce != cudaSuccess) { cudaFree(tmp); CUDA_OK(ce); }
     }
     std::vector<int> depths(plan.phaseStart.size(), 0);
     for (size_t ph = 0; ph + 1 < plan.phaseStart.size(); ++ph) depths[ph] = (maxDepth > 0 && ph < phaseDepth.size()) ? phaseDepth[ph] : 0;
-    cudaError_t e = launchPlan(in, dOps, dSubs, plan.phaseStart, depths, fourPath, maxWindow, preOrder);
+    cudaError_t e = launchPlan(in, dOps, dSubs, plan.phaseStart, depths, fourPath, maxWindow, preOrder,
+                               fourPath ? eigenFormSlot(in, hops) : -1, !byPartition);
+    if (e == cudaSuccess) e = accumulateInList(in, cumGroups);
+    noteScaleWrites(in, hops);
     if (e == cudaSuccess && tmp == nullptr && in->planCacheSize > 0) {
         // remember the plan: device copy of the records (stream-ordered D2D out of the staging ring)
         if ((int)in->planCache.size() < in->planCacheSize) in->planCache.emplace_back();
-        CachedPlan* slot = &in->planCache[0];
-        for (CachedPlan& cp : in->planCache) if (cp.dBlock == nullptr || cp.lastUse < slot->lastUse) slot = &cp;
+        CachedPlan* slot = nullptr;            // first empty slot, else the least recently used entry
+        for (CachedPlan& cp : in->planCache) {
+            if (cp.dBlock == nullptr || cp.n < 0) { slot = &cp; break; }
+            if (slot == nullptr || cp.lastUse < slot->lastUse) slot = &cp;
+        }
         const size_t subsOffset = (opBytes + 255) & ~size_t(255);
         const size_t need = subsOffset + subBytes;
         if (slot->graphExec) { cudaGraphExecDestroy(slot->graphExec); slot->graphExec = nullptr; }
         slot->hits = 0;
         slot->graphFailed = false;
+        slot->graphInvalidations = 0;
         if (slot->capacity < need) {
             if (slot->dBlock) cudaFree(slot->dBlock);
             slot->dBlock = nullptr; slot->capacity = 0;
@@ -708,6 +787,8 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             slot->subsOffset = subsOffset; slot->phaseStart = plan.phaseStart; slot->phaseDepth = depths;
             slot->fourPath = fourPath; slot->maxWindow = maxWindow; slot->preOrder = preOrder;
             slot->lastUse = ++in->planClock;
+            slot->cumGroups = cumGroups;
+            slot->graphFailed = !cumGroups.empty();      // the accumulate launches stage fresh index arrays: never captured
         } else if (slot->dBlock != nullptr) {
             slot->n = -1;
         }
@@ -724,7 +805,11 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
 // ==============================================================================================
 extern "C" {
 
-const char* beagleGetVersion(void) { return "4.0.1-b200"; }
+#ifndef B200_SOURCE_HASH
+#define B200_SOURCE_HASH "unhashed"
+#endif
+const char* beagleGetVersion(void) { return "4.0.1-b200+" B200_SOURCE_HASH; }
+const char* b200GetSourceHash(void) { return B200_SOURCE_HASH; }
 
 const char* beagleGetCitation(void) {
     return "B200-native tree-likelihood engine exposing the BEAGLE API.\n"
@@ -800,6 +885,14 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->partials.assign(in->nBuffers, nullptr);
     in->states8.assign(in->nBuffers, nullptr);
     in->states32.assign(in->nBuffers, nullptr);
+    in->scaleIsLog.assign(std::max(1, in->nScale), in->logScalers ? 1 : 0);
+    in->matEigen.assign(std::max(1, in->nMatrices), -1);
+    in->matEigenGen.assign(std::max(1, in->nMatrices), 0u);
+    in->eigenGen.assign(std::max(1, in->nEigen), 0u);
+    in->eigenReal.assign(std::max(1, in->nEigen), 0);
+    in->hEigen.assign((size_t)std::max(1, in->nEigen) * 36, 0.0);
+    in->eigenWalk = envInt("B200_EIGEN_WALK", 1);
+    in->tipMode = envInt("B200_TIP_MODE", 0);
     in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 0);
     in->reorder = envInt("B200_REORDER", 1);
@@ -821,7 +914,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->genericMma = envInt("B200_GENERIC_MMA", 1);
     in->mmaWarps = envInt("B200_MMA_WARPS", 4) == 8 ? 8 : 4;     // 8 = 256-thread blocks with cp.async double buffering
     in->walkR = envInt("B200_WALK_R", 4);
-    if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4) in->walkR = 4;
+    if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4 && in->walkR != 8) in->walkR = 4;
     if (getenv("B200_WALK_R") == nullptr && in->matCP > 0) {
         // patterns per thread: as many as still leave >= 2 warps per SM inside ONE subtree walk
         const int G = 32 / in->matCP;
@@ -846,6 +939,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     };
     alloc(&in->dEigen, std::max(1, in->nEigen) * eigenStride);
     alloc(&in->dMat, matElems);
+    if (in->matCP > 0) alloc(&in->dEvec, (size_t)in->nMatrices * in->matCP * 4);
     alloc(&in->dRates, (size_t)in->nSets * in->C);
     alloc(&in->dWeights, (size_t)in->nSets * in->C);
     alloc(&in->dFreqs, (size_t)in->nSets * in->Sp);
@@ -1036,6 +1130,22 @@ int beagleSetEigenDecomposition(int instance, int eigenIndex, const double* inEi
     memcpy(pack.data(), inEigenVectors, sizeof(double) * S * S);
     memcpy(pack.data() + S * S, inInverseEigenVectors, sizeof(double) * S * S);
     memcpy(pack.data() + 2 * S * S, inEigenValues, sizeof(double) * (in->complexEigen ? 2 * S : S));
+    if (in->matCP > 0) {
+        // host copy for the eigen-form walk (V, V^-1 travel by value in its launch); the generation only moves when the
+        // content does, so that re-uploading an unchanged system keeps captured graphs valid
+        double h[36] = {0.0};                 // V | V^-1 | eigenvalues (compared, not passed on)
+        for (size_t k = 0; k < S; ++k) h[32 + k] = inEigenValues[k];
+        for (size_t i = 0; i < S; ++i)
+            for (size_t k = 0; k < S; ++k) { h[4 * i + k] = inEigenVectors[i * S + k]; h[16 + 4 * i + k] = inInverseEigenVectors[i * S + k]; }
+        bool real = true;
+        if (in->complexEigen) for (size_t k = 0; k < S; ++k) real = real && inEigenValues[S + k] == 0.0;
+        double* dst = in->hEigen.data() + (size_t)eigenIndex * 36;
+        if (memcmp(dst, h, sizeof h) != 0 || in->eigenGen[eigenIndex] == 0 || (bool)in->eigenReal[eigenIndex] != real) {
+            memcpy(dst, h, sizeof h);
+            in->eigenGen[eigenIndex]++;
+        }
+        in->eigenReal[eigenIndex] = real ? 1 : 0;
+    }
     return uploadSmall(in, in->dEigen + (size_t)eigenIndex * stride, pack.data(), sizeof(double) * stride);
 }
 
@@ -1111,6 +1221,12 @@ static int updateMatricesImpl(Instance* in, const int* eigenIndices, int eigenIn
         pack[count + k] = e;
         pack[2 * (size_t)count + k] = r;
     }
+    if (in->matCP > 0)
+        for (int k = 0; k < count; ++k) {
+            const int e = eigenIndices ? eigenIndices[k] : eigenIndexScalar;
+            in->matEigen[probabilityIndices[k]] = e;
+            in->matEigenGen[probabilityIndices[k]] = in->eigenGen[e];
+        }
     memcpy(block.data(), edgeLengths, sizeof(double) * count);
     double* dLen = static_cast<double*>(stage(in, block.data(), sizeof(double) * block.size()));
     if (dLen == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
@@ -1148,6 +1264,7 @@ static inline size_t matIndex(const Instance* in, int c, int i, int j) {
 int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMatrix, double) {
     GET_INSTANCE(in, instance);
     if (!validRange(matrixIndex, in->nMatrices)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (in->matCP > 0) in->matEigen[matrixIndex] = -1;        // set directly: no spectrum, matrix-form kernel only
     const size_t n = in->matStride;
     std::vector<double> t(n, 0.0);
     for (int c = 0; c < in->C; ++c)
@@ -1316,6 +1433,7 @@ static int accumulateImpl(Instance* in, const int* scaleIndices, int count, int 
     if (dIdx == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
     TimedScope ts(in, T_ROOT);
     CUDA_OK(launchScaleAccumulate(in, dIdx, count, in->dScale + (size_t)cum * in->Ppad, sign, pBegin, pEnd));
+    in->scaleIsLog[cum] = 1;
     return BEAGLE_SUCCESS;
 }
 
@@ -1349,6 +1467,7 @@ int beagleResetScaleFactors(int instance, int cumulativeScaleIndex) {
     GET_INSTANCE(in, instance);
     if (!validRange(cumulativeScaleIndex, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
     CUDA_OK(cudaMemsetAsync(in->dScale + (size_t)cumulativeScaleIndex * in->Ppad, 0, sizeof(double) * in->Ppad, in->stream));
+    in->scaleIsLog[cumulativeScaleIndex] = 1;      // a cumulative buffer: sums of logs from here on
     return BEAGLE_SUCCESS;
 }
 
@@ -1359,6 +1478,7 @@ int beagleResetScaleFactorsByPartition(int instance, int cumulativeScaleIndex, i
     int b = in->partBegin[partitionIndex], e = in->partEnd[partitionIndex];
     if (e > b)
         CUDA_OK(cudaMemsetAsync(in->dScale + (size_t)cumulativeScaleIndex * in->Ppad + b, 0, sizeof(double) * (e - b), in->stream));
+    in->scaleIsLog[cumulativeScaleIndex] = 1;
     return BEAGLE_SUCCESS;
 }
 
@@ -1368,6 +1488,7 @@ int beagleCopyScaleFactors(int instance, int destScalingIndex, int srcScalingInd
         return BEAGLE_ERROR_OUT_OF_RANGE;
     CUDA_OK(cudaMemcpyAsync(in->dScale + (size_t)destScalingIndex * in->Ppad, in->dScale + (size_t)srcScalingIndex * in->Ppad,
                             sizeof(double) * in->Ppad, cudaMemcpyDeviceToDevice, in->stream));
+    in->scaleIsLog[destScalingIndex] = in->scaleIsLog[srcScalingIndex];
     return BEAGLE_SUCCESS;
 }
 
@@ -1384,7 +1505,8 @@ int beagleGetLogScaleFactors(int instance, int srcScalingIndex, double* outLogSc
     int rc = beagleGetScaleFactors(instance, srcScalingIndex, outLogScaleFactors);
     if (rc != BEAGLE_SUCCESS) return rc;
     Instance* in = getInstance(instance);
-    if (!in->logScalers)
+    // per-node buffers hold raw factors under SCALERS_RAW; cumulative buffers (reset / accumulate / in-list) always hold logs
+    if (!in->scaleIsLog[srcScalingIndex])
         for (int p = 0; p < in->P; ++p) outLogScaleFactors[p] = log(outLogScaleFactors[p]);
     return BEAGLE_SUCCESS;
 }

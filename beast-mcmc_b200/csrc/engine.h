@@ -55,8 +55,11 @@ struct EdgeRef { const double* post; const int* states; const double* pre; const
 
 // a remembered execution plan: the caller's list (key) and its device-resident op records + subtree table
 struct HostOp { int dest, sw, sr, c1, m1, c2, m2, part, cum; int kind = 0; };   // kind 1 = pre-order op
+// in-list cumulative scaling of an updatePartials call: cum[p] += sum over `indices` of log factor[p] on [pBegin, pEnd)
+struct CumGroup { int cum, pBegin, pEnd; std::vector<int> indices; };
 struct CachedPlan {
     std::vector<HostOp> key;
+    std::vector<CumGroup> cumGroups;
     int n = -1;
     bool byPartition = false, fourPath = false, preOrder = false;
     unsigned long epoch = 0;
@@ -68,6 +71,9 @@ struct CachedPlan {
     long hits = 0;
     cudaGraphExec_t graphExec = nullptr;      // the plan's phase launches as one graph launch (plans with >= 2 launches)
     bool graphFailed = false;                 // capture or instantiation failed once: plain launches from then on
+    int graphEigen = -2;                      // eigen slot / generation the captured launches carry by value (-1: matrix form)
+    unsigned graphEigenGen = 0;
+    int graphInvalidations = 0;
 };
 
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
@@ -96,10 +102,21 @@ struct Instance {
 
     double* dEigen = nullptr;                 // [nEigen][2*S*S + 2*S]
     double* dMat = nullptr;                   // [nMatrices][C][Sp][Sp] transposed
+    double* dEvec = nullptr;                  // 4-state path: [nMatrices][CP][4] spectra exp(lambda_k r_c t) (walk4e.cu)
+    // provenance of every matrix buffer: the eigen slot and its generation at updateTransitionMatrices time (-1 = set
+    // directly / convolved); the eigen-form walk serves a list only while all its matrices stem from the CURRENT content
+    // of one real eigen slot
+    std::vector<int> matEigen;
+    std::vector<unsigned> matEigenGen, eigenGen;
+    std::vector<char> eigenReal;
+    std::vector<double> hEigen;               // [nEigen][32]: V | V^-1 padded to 4 x 4 (host copy, by value into the launch)
+    int eigenWalk = 1;                        // B200_EIGEN_WALK: 0 = always the matrix-form kernel
+    int tipMode = 0;                          // B200_TIP_MODE: eigen-form walk, compact tips by contraction (0) or P column (1)
     double* dRates = nullptr;                 // [nSets][C]
     double* dWeights = nullptr;               // [nSets][C]
     double* dFreqs = nullptr;                 // [nSets][Sp]
     double* dScale = nullptr;                 // [nScale][Ppad]
+    std::vector<char> scaleIsLog;             // per scale buffer: holds logarithms (cumulative buffers always do)
     double* dPatternWeights = nullptr;        // [Ppad], zero padded
     int* dPatternPartitions = nullptr;        // [Ppad]
     double* dSite = nullptr;                  // [Ppad]
@@ -155,6 +172,9 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
                                      const int* dRateSet, const double* dLengths, int count);
 // dSubs[k] = (first op, one-past-last op, first pattern, one-past-last pattern) of subtree walk k
 cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder);
+// walk4e.cu: eigen-form 4-state walk; eigen = [V (16) | V^-1 (16)]; aligned = every op covers [0, Ppad)
+cudaError_t launchWalk4E(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int maxWindow, bool aligned,
+                         const double* eigen);
 cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow, bool preOrder);
 // `partial`: edgeDerivativeWorkspace() doubles when that is non-zero (tensor-pipe form), else nullptr
 size_t edgeDerivativeWorkspace(const Instance* in, int count);

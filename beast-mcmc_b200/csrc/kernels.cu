@@ -15,27 +15,11 @@
 // operand stack), not from HBM.  The only mandatory HBM traffic is the write of every destination
 // buffer (BEAST needs them for later incremental updates) plus tips and pre-existing siblings.
 #include "engine.h"
+#include "walk4.cuh"
 
 #include <cfloat>
 
 namespace b200 {
-
-// ---------------------------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldg256(const double* p, double (&v)[4]) {
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
-}
-// read-only path for data produced by an EARLIER launch (matrices)
-__device__ __forceinline__ void ldg256_nc(const double* p, double (&v)[4]) {
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
-__device__ __forceinline__ void stg256(double* p, const double (&v)[4]) {
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
-}
 
 // fp64 tensor-core primitive (SASS DMMA.8x8x4): D(8x8) += A(8x4) * B(4x8); lane (g = lane/4, t = lane%4)
 // holds A[g][t], B[t][g] and D[g][2t], D[g][2t+1]
@@ -53,7 +37,7 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
                              int complexForm, const double* __restrict__ ratesBase,
                              const int* __restrict__ probIdx, const int* __restrict__ eigenIdx,
                              const int* __restrict__ rateSet, const double* __restrict__ lengths,
-                             double* __restrict__ matBase, size_t matStride, int matCP) {
+                             double* __restrict__ matBase, size_t matStride, int matCP, double* __restrict__ evecBase) {
     extern __shared__ double sm[];
     double* ec = sm;
     double* ss = sm + S;
@@ -83,6 +67,9 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
         }
     }
     __syncthreads();
+    // the branch's spectrum exp(lambda_k r_c t) for the eigen-form walk (walk4e.cu): [matrix][CP][4]
+    if (evecBase != nullptr && threadIdx.x < 4)
+        evecBase[((size_t)probIdx[b] * matCP + c) * 4 + threadIdx.x] = threadIdx.x < S ? ec[threadIdx.x] : 0.0;
     // generic layout [c][j][i]; 4-state layout [j][CP][i] (one 128-byte line holds row j of all categories)
     double* out = matBase + (size_t)probIdx[b] * matStride + (matCP ? (size_t)c * 4 : (size_t)c * Sp * Sp);
     const int rowStride = matCP ? matCP * 4 : Sp;
@@ -211,7 +198,7 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
     k_transition<<<grid, threads, smem, in->stream>>>(in->dEigen, 2 * (size_t)in->S * in->S + 2 * in->S, in->S,
                                                       in->Sp, in->C, in->complexEigen ? 1 : 0, in->dRates,
                                                       dProbIdx, dEigenIdx, dRateSet, dLengths, in->dMat,
-                                                      in->matStride, in->matCP);
+                                                      in->matStride, in->matCP, in->matCP ? in->dEvec : nullptr);
     return cudaGetLastError();
 }
 
@@ -229,40 +216,6 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
 //     optional variant (B200_WALK_VARIANT=1): a per-thread operand stack in shared memory for every such child,
 //     laid out [slot][half][thread] so every LDS.128/STS.128 is bank-conflict free
 //   * tip states: one byte per pattern; their line is prefetched one op ahead
-struct WalkArgs {
-    const Op4* ops;
-    const int4* subs;          // [subtree] = (first op, one-past-last op, first pattern, one-past-last pattern)
-    double* partials;          // slab base
-    size_t stride;             // elements per slot
-    const uint8_t* states;     // [tip][Ppad]
-    const double* mats;        // [matrix][4][CP][4]
-    double* scale;             // [buffer][Ppad]
-    int S, C, Ppad, logScalers;
-    size_t matStride;          // elements per matrix buffer
-    int matMmaOffset;          // offset of the [c][i][j] + [c][j][i] copies inside a matrix buffer
-};
-
-__device__ __forceinline__ Op4 loadOp(const Op4* p) {
-    const int4* q = reinterpret_cast<const int4*>(p);
-    int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-    Op4 o;
-    o.dest = a.x; o.c1 = a.y; o.c2 = a.z; o.m1 = a.w;
-    o.m2 = b.x; o.sw = b.y; o.sr = b.z; o.cum = b.w;
-    o.pBegin = c.x; o.pEnd = c.y; o.slots = (unsigned)c.z; o.pad_ = c.w;
-    o.pfA = d.x; o.pfB = d.y; o.pfM1 = d.z; o.pfM2 = d.w;
-    return o;
-}
-
-__device__ __forceinline__ void prefetchL1(const void* p) {
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-}
-
-// non-volatile: a read-only load the scheduler may hoist freely
-__device__ __forceinline__ void ldg256_ro(const double* p, double (&v)[4]) {
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-        : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
-
 struct Mat4 { double r[4][4]; };     // r[j][i] = P[i][j] of this thread's category
 
 template <int CP>
@@ -440,14 +393,9 @@ k_walk4(const WalkArgs A) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) d[r][i] *= inv;
                 if (active && c == 0) {
-                    // BEAST's protocol (raw scalers, accumulation in a separate call) needs no logarithm here
-                    if (A.logScalers || cur.cum >= 0) {
-                        const double lm = log(m);
-                        A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
-                        if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
-                    } else {
-                        A.scale[(size_t)cur.sw * A.Ppad + p] = m;
-                    }
+                    // raw scalers need no logarithm here; cumulative buffers are accumulated by k_scale_accum after the
+                    // phases (an in-walk "cum += log m" would race between concurrent subtrees)
+                    A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? log(m) : m;
                 }
                 __syncwarp();
             } else if (cur.sr >= 0) {
@@ -585,9 +533,7 @@ k_walk4t(const WalkArgs A) {
                     if (m == 0.0) m = 1.0;
                     f = m;
                     if (act && t == 0) {
-                        const double lm = log(m);
-                        A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? lm : m;
-                        if (cur.cum >= 0) A.scale[(size_t)cur.cum * A.Ppad + p] += lm;
+                        A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? log(m) : m;
                     }
                 } else {
                     f = act ? A.scale[(size_t)cur.sr * A.Ppad + p] : 1.0;
@@ -798,9 +744,7 @@ k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int
                     if (p < op.pBegin || p >= op.pEnd || p >= range.w) continue;
                     double m = __longlong_as_double((long long)pmax[pl]);
                     if (m == 0.0) m = 1.0;
-                    const double lm = log(m);
-                    op.scaleWrite[p] = logScalers ? lm : m;
-                    if (op.cumScale) op.cumScale[p] += lm;
+                    op.scaleWrite[p] = logScalers ? log(m) : m;
                 }
             }
             __syncthreads();
@@ -1054,9 +998,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                     if (mx == 0.0) mx = 1.0;
                     f = mx;
                     if (act[m] && t == 0) {
-                        const double lm = log(mx);
-                        op.scaleWrite[p] = logScalers ? lm : mx;
-                        if (op.cumScale) op.cumScale[p] += lm;
+                        op.scaleWrite[p] = logScalers ? log(mx) : mx;
                     }
                 } else {
                     f = act[m] ? op.scaleRead[p] : 1.0;

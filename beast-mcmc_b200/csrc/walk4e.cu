@@ -1,0 +1,237 @@
+// walk4e.cu -- the 4-state (nucleotide) walk in EIGEN FORM: the default updatePartials kernel of S <= 4 instances.
+//
+// What bounded k_walk4 (profiles/r01_ncu_raw.txt, source page of the same capture): the L1/LSU data pipe at 70 % of peak
+// wavefronts, 60 % of them matrix traffic -- every thread needs its category's 4x4 matrix in registers (128 B per child)
+// and a compact-tip child costs one 32-B matrix column per PATTERN -- while HBM only saw the mandatory destination writes.
+//
+// Here no transition matrix is read at all.  With one real eigen system per list (what HomogenousSubstitutionModelDelegate
+// hands over, HSMD:228-266)
+//        P_c(t) x = V ( e ⊙ (V^-1 x) ),     e_k = exp(lambda_k r_c t)
+// so a branch is 4 doubles per category ("spectrum", written by k_transition next to the matrices) and V, V^-1 are the same
+// for every op of the launch: they travel BY VALUE in the kernel parameters, i.e. in the constant bank, and reach the FP64
+// pipe as uniform-register operands (SASS: LDCU.128 + DFMA R, R, UR, R) -- zero registers, zero LSU wavefronts.
+//   internal child : u = V^-1 x (16 FMA), w = e ⊙ u (4), y = |V w| (16)        -- 32 B of spectrum instead of 128 B of matrix
+//   compact tip    : u_k = V^-1[k][s] (register selects on the state byte), then as above; gap/unknown -> y = 1
+// |.| mirrors the reference's abs() on P(t) entries (BaseSubstitutionModel.java:236): for a tip the value IS |P[i][s]|
+// with the reference's own summation order; partials stay non-negative.  The FP64 pipe goes from 12 % to ~40 % busy; the
+// LSU data pipe keeps only what is irreducible: destination stores, the child cells that are not forwarded in registers,
+// spectra, op records.  Lists the form does not cover (matrices set directly or convolved, complex pairs, several eigen
+// systems in one list) run on k_walk4; pre-order lists keep their own kernel.  Results agree with the matrix form to
+// rounding (tests/test_gpu_parity.py::test_walk_variants_agree, 1e-13).
+//
+// ALIGNED = every op spans whole 32-pattern groups [0, Ppad): no per-pattern predicates at all (padded columns hold
+// harmless finite values and are never read back).  Partition windows take the predicated instance.
+#include "engine.h"
+#include "walk4.cuh"
+
+namespace b200 {
+
+namespace {
+
+// TIP = 0: a compact-tip child goes through the same contraction with a one-hot x (no memory traffic, no extra code path);
+// TIP = 1: its value is column s of the stored P matrix (one 32-B load per pattern, no arithmetic) -- the LSU / FP64
+//          trade-off is measured, not guessed (B200_TIP_MODE)
+template <int CP, int R, bool ALIGNED, bool FIRST, int TIP>
+__device__ __forceinline__ void childTermE(const WalkArgs& A, const double (&Vi)[16], int child, int matIdx, bool fromRegisters,
+                                           int cc, size_t off0, int p0, bool catValid, int pBegin, int pEnd, double (&d)[R][4]) {
+    constexpr int G = 32 / CP;
+    const int S = A.S;
+    const bool tip = child < 0;
+    if (TIP == 1 && tip) {
+        const uint8_t* t = A.states + (size_t)(-child - 1) * A.Ppad;
+        const double* m = A.mats + (size_t)matIdx * A.matStride + cc * 4;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r * G;
+            const int s = (ALIGNED || (catValid && p >= pBegin && p < pEnd)) ? (int)__ldg(t + p) : S;
+            double v[4];
+            if (s < S) ldg256_ro(m + 4 * CP * s, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = (i < S) ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[r][i] = FIRST ? v[i] : d[r][i] * v[i];
+        }
+        return;
+    }
+    double e[4];
+    ldg256_ro(A.evecs + ((size_t)matIdx * CP + cc) * 4, e);
+    const uint8_t* t = A.states + (size_t)(tip ? -child - 1 : 0) * A.Ppad;
+    const double* xg = A.partials + (size_t)(tip ? 0 : child) * A.stride + off0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int p = p0 + r * G;
+        const bool live = ALIGNED || (catValid && p >= pBegin && p < pEnd);
+        double x[4], u[4], y[4];
+        int s = 0;
+        if (tip) {
+            s = live ? (int)__ldg(t + p) : S;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = (s == j) ? 1.0 : 0.0;
+        } else if (fromRegisters) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = d[r][i];
+        } else if (live) {
+            ldg256(xg + (size_t)r * G * 4, x);
+        } else {
+            x[0] = x[1] = x[2] = x[3] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            u[k] = (Vi[4 * k] * x[0] + Vi[4 * k + 1] * x[1] + Vi[4 * k + 2] * x[2] + Vi[4 * k + 3] * x[3]) * e[k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            y[i] = fabs(A.V[4 * i] * u[0] + A.V[4 * i + 1] * u[1] + A.V[4 * i + 2] * u[2] + A.V[4 * i + 3] * u[3]);
+        if (tip && s >= S) {                                       // gap / unknown: every state is compatible
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = (i < S) ? 1.0 : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[r][i] = FIRST ? y[i] : d[r][i] * y[i];
+    }
+}
+
+template <int CP, int R, bool ALIGNED, int MINB, int TIP>
+__global__ void __launch_bounds__(128, MINB)
+k_walk4e(const WalkArgs A) {
+    constexpr int G = 32 / CP;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int c = lane / G;
+    const int4 range = __ldg(A.subs + blockIdx.y);
+    const int p0 = range.z + warp * (G * R) + (lane % G);          // patterns p0 + r*G
+    if (range.z + warp * (G * R) >= range.w) return;               // whole warp outside this subtree's pattern window
+    const bool catValid = c < A.C;
+    const int cc = catValid ? c : 0;
+    const size_t off0 = ((size_t)cc * A.Ppad + p0) * 4;
+    const int last = range.y - 1;
+
+    // V^-1 in vector registers (the tip selects and the first contraction read it), V stays in the constant bank: both in
+    // uniform registers do not fit (64 > 63) and ptxas would spill.  The asm keeps ptxas from folding the copy back.
+    double Vi[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) asm volatile("mov.f64 %0, %1;" : "=d"(Vi[q]) : "d"(A.Vi[q]));
+    Op4 cur = loadOp(A.ops + range.x);
+    double d[R][4];                                                // survives the loop: op k+1 may take it as its first child
+#pragma unroll
+    for (int r = 0; r < R; ++r) d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.0;
+    for (int k = range.x; k <= last; ++k) {
+        Op4 nxt;
+        if (R == 1) nxt = loadOp(A.ops + min(k + 1, last));
+        else if (lane == 0) prefetchL1(A.ops + min(k + 2, last));
+        // look-ahead: what the NEXT op reads from memory (never this op's destination) starts its trip to L1 now
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int pf = w == 0 ? cur.pfA : cur.pfB;
+            if (pf == 0) continue;
+            if (pf & 1) {
+                const uint8_t* t = A.states + (size_t)(pf >> 1) * A.Ppad + p0;
+                if ((lane % G) == 0 && c == 0) prefetchL1(t);                  // G*R consecutive bytes: one line
+            } else if (catValid) {
+                const double* xg = A.partials + (size_t)((pf >> 1) - 1) * A.stride + off0;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (p0 + r * G < A.Ppad) prefetchL1(xg + (size_t)r * G * 4);
+            }
+        }
+        if (lane < 2) {
+            const int mi = lane == 0 ? cur.pfM1 : cur.pfM2;
+            if (mi >= 0) prefetchL1(A.evecs + (size_t)mi * CP * 4);            // all categories of a branch: one 128-B line
+        }
+        childTermE<CP, R, ALIGNED, true, TIP>(A, Vi, cur.c1, cur.m1, (cur.pad_ & 2) != 0, cc, off0, p0, catValid, cur.pBegin, cur.pEnd, d);
+        childTermE<CP, R, ALIGNED, false, TIP>(A, Vi, cur.c2, cur.m2, false, cc, off0, p0, catValid, cur.pBegin, cur.pEnd, d);
+        if (R != 1) nxt = loadOp(A.ops + min(k + 1, last));
+        double* dg = A.partials + (size_t)cur.dest * A.stride + off0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r * G;
+            const bool active = ALIGNED ? catValid : (catValid && p >= cur.pBegin && p < cur.pEnd);
+            // ---- rescaling (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE) -----
+            if (cur.sw >= 0) {
+                double m = active ? fmax(fmax(d[r][0], d[r][1]), fmax(d[r][2], d[r][3])) : 0.0;
+#pragma unroll
+                for (int sh = G; sh < 32; sh <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, sh));
+                if (m == 0.0) m = 1.0;
+                const double inv = 1.0 / m;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[r][i] *= inv;
+                if (active && c == 0) A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? log(m) : m;
+            } else if (cur.sr >= 0) {
+                double f = active ? A.scale[(size_t)cur.sr * A.Ppad + p] : 1.0;
+                if (A.logScalers) f = exp(f);
+                const double inv = 1.0 / f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[r][i] *= inv;
+            }
+            if (active) stg256(dg + (size_t)r * G * 4, d[r]);
+        }
+        cur = nxt;
+    }
+}
+
+template <int CP, int R, bool ALIGNED, int MINB, int TIP>
+cudaError_t launchK(Instance* in, const WalkArgs& A, dim3 grid) {
+    k_walk4e<CP, R, ALIGNED, MINB, TIP><<<grid, 128, 0, in->stream>>>(A);
+    return cudaGetLastError();
+}
+
+// shipped configuration per category count: R in {1, 4} x {aligned, windows}; CP = 4 (the Gamma-4 workloads the metric is
+// quoted on) additionally carries the tuning space behind B200_WALK_R / B200_WALK_MINB / B200_TIP_MODE
+template <int CP, int R>
+cudaError_t launchR(Instance* in, WalkArgs& A, int nSubs, int maxWindow, bool aligned) {
+    constexpr int G = 32 / CP;
+    const int warps = (maxWindow + G * R - 1) / (G * R);
+    dim3 grid((warps + 3) / 4, nSubs);
+    if (!aligned) return launchK<CP, R, false, 4, 0>(in, A, grid);
+    if constexpr (CP == 4 && R >= 2) {
+        const int minb = in->walkMinBlocks, tip = in->tipMode;
+        if (tip == 1) {
+            if (minb >= 5) return launchK<CP, R, true, 5, 1>(in, A, grid);
+            if (minb == 3) return launchK<CP, R, true, 3, 1>(in, A, grid);
+            return launchK<CP, R, true, 4, 1>(in, A, grid);
+        }
+        if (minb >= 5) return launchK<CP, R, true, 5, 0>(in, A, grid);
+        if (minb == 3) return launchK<CP, R, true, 3, 0>(in, A, grid);
+    }
+    return launchK<CP, R, true, 4, 0>(in, A, grid);
+}
+
+template <int CP>
+cudaError_t launchCP(Instance* in, WalkArgs& A, int nSubs, int maxWindow, bool aligned) {
+    // a thin phase (few walks in flight) is latency-bound: one pattern group per thread gives the most warps per op
+    const long walks = (long)nSubs * ((maxWindow + (32 / CP) * in->walkR - 1) / ((32 / CP) * in->walkR));
+    if ((in->thinR1 && walks < (long)in->smCount * 8) || in->walkR == 1) return launchR<CP, 1>(in, A, nSubs, maxWindow, aligned);
+    if constexpr (CP == 4) {
+        if (in->walkR == 8) return launchR<CP, 8>(in, A, nSubs, maxWindow, aligned);
+        if (in->walkR == 2) return launchR<CP, 2>(in, A, nSubs, maxWindow, aligned);
+    }
+    return launchR<CP, 4>(in, A, nSubs, maxWindow, aligned);
+}
+
+}  // namespace
+
+// eigen: [V (16, row-major Evec[i][k]) | V^-1 (16, Ievc[k][j])], padded to 4 x 4 with zeros
+cudaError_t launchWalk4E(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int maxWindow, bool aligned,
+                         const double* eigen) {
+    if (nSubs <= 0) return cudaSuccess;
+    WalkArgs A;
+    A.ops = dOps; A.subs = dSubs; A.partials = in->partialsBase; A.stride = in->partialsElems;
+    A.states = in->states8Base; A.mats = in->dMat; A.scale = in->dScale;
+    A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.logScalers = in->logScalers ? 1 : 0;
+    A.matStride = in->matStride; A.matMmaOffset = 16 * in->matCP;
+    A.evecs = in->dEvec;
+    for (int q = 0; q < 16; ++q) { A.V[q] = eigen[q]; A.Vi[q] = eigen[16 + q]; }
+    switch (in->matCP) {
+#ifndef B200_W4E_QUICK
+        case 1: return launchCP<1>(in, A, nSubs, maxWindow, aligned);
+        case 2: return launchCP<2>(in, A, nSubs, maxWindow, aligned);
+        case 8: return launchCP<8>(in, A, nSubs, maxWindow, aligned);
+        case 16: return launchCP<16>(in, A, nSubs, maxWindow, aligned);
+        case 32: return launchCP<32>(in, A, nSubs, maxWindow, aligned);
+#endif
+        default: return launchCP<4>(in, A, nSubs, maxWindow, aligned);
+    }
+}
+
+}  // namespace b200

@@ -311,6 +311,10 @@ BEAGLE_DLLEXPORT int beagleGetSiteLogLikelihoods(int instance, double* outLogLik
  * which: 0 = updatePartials kernels, 1 = updateTransitionMatrices, 2 = root/scale kernels. */
 BEAGLE_DLLEXPORT int b200SetKernelTiming(int instance, int enable);
 BEAGLE_DLLEXPORT int b200GetKernelTiming(int instance, int which, double* outMilliseconds, long* outLaunches);
+/* SHA-256 prefix (16 hex digits) of the sources this binary was built from; __graft_entry__.build() and
+ * beast-mcmc_b200/build.py compare it with the tree so that a prebuilt library cannot drift from its sources.  The same
+ * string is the build-metadata suffix of beagleGetVersion ("4.0.1-b200+<hash>"). */
+BEAGLE_DLLEXPORT const char* b200GetSourceHash(void);
 /* Pinned-host staging for callers that want the H2D/D2H copies to be asynchronous. */
 BEAGLE_DLLEXPORT void* b200HostAlloc(long bytes);
 BEAGLE_DLLEXPORT void b200HostFree(void* p);

@@ -60,6 +60,9 @@ class OracleBeagle:
         self.eigen = [None] * eigenBufferCount
         self.matrices = [None] * matrixBufferCount    # each [C][S][S]
         self.scale = [np.zeros(patternCount) for _ in range(scaleBufferCount)]
+        # per-node buffers hold raw factors (logs under SCALERS_LOG); cumulative buffers -- anything touched by
+        # reset / accumulate / remove / an in-list cumulative index -- always hold logs
+        self.scaleIsLog = [self.log_scalers] * scaleBufferCount
         self.categoryRates = {0: np.ones(categoryCount)}
         self.categoryWeights = {}
         self.frequencies = {}
@@ -200,8 +203,10 @@ class OracleBeagle:
         self.partials[dest][:, sel, :] = d / m[None, :, None]
         logm = np.log(m)
         self.scale[writeIdx][sel] = logm if self.log_scalers else m
+        self.scaleIsLog[writeIdx] = self.log_scalers
         if cumIdx != NONE:
             self.scale[cumIdx][sel] += logm
+            self.scaleIsLog[cumIdx] = True
 
     def _update_one(self, op, sel, cumIdx):
         dest, sw, sr, c1, m1, c2, m2 = op[:7]
@@ -255,24 +260,35 @@ class OracleBeagle:
         for k in range(count):
             self.matrices[resultIndices[k]] = self.matrices[firstIndices[k]] + self.matrices[secondIndices[k]]
 
+    def _pre_one(self, op, sel, cumIdx):
+        dest, sw, sr, parentPre, m1, sib, m2 = op[:7]
+        q = self.partials[parentPre][:, sel, :] * self._child_term(sib, m2, sel)    # at the parent: [C][P][S(i)]
+        M1 = self.matrices[m1]                                                      # [C][i][j]
+        out = np.zeros_like(q)
+        for i in range(self.S):                                                     # down the branch: sum_i q_i M[i][j]
+            out += q[:, :, i][:, :, None] * M1[:, None, i, :]
+        if self.partials[dest] is None:
+            self.partials[dest] = np.zeros((self.C, self.P, self.S))
+        self.partials[dest][:, sel, :] = out
+        self.tipStates[dest] = None
+        if sw >= 0:
+            self._rescale(dest, sel, sw, cumIdx)
+        elif sr >= 0:
+            f = self.scale[sr][sel]
+            f = np.exp(f) if self.log_scalers else f
+            self.partials[dest][:, sel, :] /= f[None, :, None]
+
     def updatePrePartials(self, operations, operationCount, cumulativeScaleIndex):
         ops = np.asarray(operations, dtype=np.int64).reshape(-1)
-        sel = slice(None)
         for k in range(operationCount):
-            dest, sw, sr, parentPre, m1, sib, m2 = ops[7 * k: 7 * k + 7]
-            q = self.partials[parentPre] * self._child_term(sib, m2, sel)        # at the parent: [C][P][S(i)]
-            M1 = self.matrices[m1]                                              # [C][i][j]
-            out = np.zeros_like(q)
-            for i in range(self.S):                                             # down the branch: sum_i q_i M[i][j]
-                out += q[:, :, i][:, :, None] * M1[:, None, i, :]
-            self.partials[dest] = out
-            self.tipStates[dest] = None
-            if sw >= 0:
-                self._rescale(dest, sel, sw, cumulativeScaleIndex)
-            elif sr >= 0:
-                f = self.scale[sr]
-                f = np.exp(f) if self.log_scalers else f
-                self.partials[dest] /= f[None, :, None]
+            self._pre_one(ops[7 * k: 7 * k + 7], slice(None), cumulativeScaleIndex)
+
+    def updatePrePartialsByPartition(self, operations, operationCount):
+        """9-int tuples like updatePartialsByPartition; the op applies to its partition's pattern window only."""
+        ops = np.asarray(operations, dtype=np.int64).reshape(-1)
+        for k in range(operationCount):
+            op = ops[9 * k: 9 * k + 9]
+            self._pre_one(op, np.nonzero(self.patternPartitions == op[7])[0], op[8])
 
     def _post_as_partials(self, idx):
         if self.tipStates[idx] is not None:
@@ -335,34 +351,41 @@ class OracleBeagle:
 
     # ---- scale factors ------------------------------------------------------------------
     def _logf(self, idx):
-        return self.scale[idx] if self.log_scalers else np.log(self.scale[idx])
+        return self.scale[idx] if self.scaleIsLog[idx] else np.log(self.scale[idx])
 
     def accumulateScaleFactors(self, scaleIndices, count, cumulativeScaleIndex):
+        self.scaleIsLog[cumulativeScaleIndex] = True
         for k in range(count):
             self.scale[cumulativeScaleIndex] += self._logf(scaleIndices[k])
 
     def removeScaleFactors(self, scaleIndices, count, cumulativeScaleIndex):
+        self.scaleIsLog[cumulativeScaleIndex] = True
         for k in range(count):
             self.scale[cumulativeScaleIndex] -= self._logf(scaleIndices[k])
 
     def accumulateScaleFactorsByPartition(self, scaleIndices, count, cumulativeScaleIndex, partitionIndex):
+        self.scaleIsLog[cumulativeScaleIndex] = True
         sel = self.patternPartitions == partitionIndex
         for k in range(count):
             self.scale[cumulativeScaleIndex][sel] += self._logf(scaleIndices[k])[sel]
 
     def removeScaleFactorsByPartition(self, scaleIndices, count, cumulativeScaleIndex, partitionIndex):
+        self.scaleIsLog[cumulativeScaleIndex] = True
         sel = self.patternPartitions == partitionIndex
         for k in range(count):
             self.scale[cumulativeScaleIndex][sel] -= self._logf(scaleIndices[k])[sel]
 
     def resetScaleFactors(self, cumulativeScaleIndex):
+        self.scaleIsLog[cumulativeScaleIndex] = True
         self.scale[cumulativeScaleIndex][:] = 0.0
 
     def resetScaleFactorsByPartition(self, cumulativeScaleIndex, partitionIndex):
+        self.scaleIsLog[cumulativeScaleIndex] = True
         self.scale[cumulativeScaleIndex][self.patternPartitions == partitionIndex] = 0.0
 
     def copyScaleFactors(self, destScalingIndex, srcScalingIndex):
         self.scale[destScalingIndex][:] = self.scale[srcScalingIndex]
+        self.scaleIsLog[destScalingIndex] = self.scaleIsLog[srcScalingIndex]
 
     def getLogScaleFactors(self, scaleIndex, out):
         out[:] = self._logf(scaleIndex)

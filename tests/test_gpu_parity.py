@@ -181,23 +181,36 @@ def test_mcmc_reenactment_store_restore():
 
 
 def test_walk_variants_agree():
-    """FMA walk: operand-stack == direct-global == caller order, bitwise (same arithmetic).  The tensor-core
-    variant (DMMA accumulates the 4-term dot product in its own order) agrees to rounding."""
+    """Matrix-form FMA walk: operand-stack == direct-global == caller order, bitwise (same arithmetic).  The eigen-form walk
+    (the default: P x evaluated as V (e * (V^-1 x)), walk4e.cu) in its tuning variants and the tensor-core variant (DMMA
+    accumulates the 4-term dot product in its own order) agree with it to rounding."""
     import os
     tree, pats, model, site = H.synthetic_case(120, 700, 4, seed=4)
-    vals, tensor = [], []
-    for variant, reorder, depth in [("0", "0", "12"), ("0", "1", "12"), ("1", "1", "12"), ("1", "1", "2"), ("1", "0", "3"),
-                                    ("2", "1", "12"), ("2", "0", "12")]:
-        os.environ["B200_WALK_VARIANT"], os.environ["B200_REORDER"], os.environ["B200_STACK_DEPTH"] = variant, reorder, depth
+    keys = ("B200_WALK_VARIANT", "B200_REORDER", "B200_STACK_DEPTH", "B200_EIGEN_WALK", "B200_WALK_R", "B200_TIP_MODE",
+            "B200_WALK_MINB")
+
+    def run(**env):
+        for k, v in env.items():
+            os.environ[k] = v
         try:
             d = _delegate(tree, pats, model, site, GPU, rescalingScheme=S_.ALWAYS, delayRescalingUntilUnderflow=False)
-            (tensor if variant == "2" else vals).append(tdl.TreeDataLikelihood(d, tree).getLogLikelihood())
+            v = tdl.TreeDataLikelihood(d, tree).getLogLikelihood()
             d.finalize()
+            return v
         finally:
-            for k in ("B200_WALK_VARIANT", "B200_REORDER", "B200_STACK_DEPTH"):
+            for k in keys:
                 os.environ.pop(k, None)
+
+    vals = [run(B200_EIGEN_WALK="0", B200_WALK_VARIANT=v, B200_REORDER=r, B200_STACK_DEPTH=dp)
+            for v, r, dp in [("0", "0", "12"), ("0", "1", "12"), ("1", "1", "12"), ("1", "1", "2"), ("1", "0", "3")]]
     assert all(v == vals[0] for v in vals), vals
+    tensor = [run(B200_WALK_VARIANT="2", B200_REORDER=r) for r in ("1", "0")]
+    eigen = [run(), run(B200_REORDER="0"), run(B200_WALK_R="1"), run(B200_WALK_R="2"), run(B200_WALK_R="8"),
+             run(B200_TIP_MODE="1"), run(B200_TIP_MODE="1", B200_WALK_MINB="5"), run(B200_WALK_MINB="3")]
     assert all(_rel(v, vals[0]) <= 1e-13 for v in tensor), (tensor, vals[0])
+    assert all(_rel(v, vals[0]) <= 1e-13 for v in eigen), (eigen, vals[0])
+    # same arithmetic whatever the tiling: the eigen-form variants with the contraction for tips are bit-identical
+    assert len({eigen[k] for k in (0, 1, 2, 3, 4, 7)}) == 1, eigen
 
 
 def test_by_partition_equals_separate_instances():

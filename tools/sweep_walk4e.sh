@@ -1,0 +1,26 @@
+#!/bin/bash
+# Variant sweep of the eigen-form 4-state walk (walk4e.cu) against the matrix-form kernel, one digest line per setting.
+#   usage (GPU box):  bash tools/sweep_walk4e.sh [workload] [out-file]
+W=${1:-gtr_g4_1000x10k}
+OUT=${2:-gpurun_out/r02_sweep_walk4e.txt}
+mkdir -p gpurun_out
+python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1     # alignment cache
+: > $OUT
+run() {   # label, env assignments...
+  local label=$1; shift
+  echo -n "$label | " >> $OUT
+  env "$@" python tools/bench_line.py --workload $W --steps ${STEPS:-200} --warmup 10 --no-cpu-baseline >> $OUT 2>&1
+}
+run "matrix form k_walk4 (round 1)    " B200_EIGEN_WALK=0
+run "eigen R4 minb4 tip=contraction   " B200_EIGEN_WALK=1
+run "eigen R4 minb5 tip=contraction   " B200_WALK_MINB=5
+run "eigen R4 minb3 tip=contraction   " B200_WALK_MINB=3
+run "eigen R8 minb4 tip=contraction   " B200_WALK_R=8
+run "eigen R8 minb3 tip=contraction   " B200_WALK_R=8 B200_WALK_MINB=3
+run "eigen R2 minb5 tip=contraction   " B200_WALK_R=2 B200_WALK_MINB=5
+run "eigen R4 minb4 tip=P column      " B200_TIP_MODE=1
+run "eigen R4 minb5 tip=P column      " B200_TIP_MODE=1 B200_WALK_MINB=5
+run "eigen R8 minb3 tip=P column      " B200_TIP_MODE=1 B200_WALK_R=8 B200_WALK_MINB=3
+run "eigen R4 minb5 no look-ahead     " B200_WALK_MINB=5 B200_LOOKAHEAD=0
+run "eigen R4 minb5 oversub 2         " B200_WALK_MINB=5 B200_PHASE_OVERSUB=2
+cat $OUT
