@@ -166,6 +166,10 @@ _SIGNATURES = {
     "b200GetKernelTiming": ([_I, _I, _DP, C.POINTER(C.c_long)], _I),
     "b200CompressSitePatterns": ([_I, _I, _I, _IP, _DP, _IP, _IP, _DP, _IP], _I),
     "b200GetSourceHash": ([], C.c_char_p),
+    "b200SetShardDevices": ([_IP, _I], _I),
+    "b200ExchangeConnectLocal": ([_IP, _I], _I),
+    "b200ExchangeCreate": ([_I, _I, _I, C.c_void_p], _I),
+    "b200ExchangeConnect": ([_I, C.c_void_p], _I),
     "b200HostAlloc": ([_L], C.c_void_p),
     "b200HostFree": ([C.c_void_p], None),
     "b200DebugPlan": ([_I if False else _IP, _I, _I, _I, _I, _I, _I, _I, _IP, _IP, _IP, _IP], _I),

@@ -8,8 +8,10 @@
 // BEAGLE_ERROR_NO_RESOURCE.
 #include "../../include/libhmsbeagle_b200.h"
 #include "engine.h"
+#include "multi.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -42,9 +44,21 @@ Instance* getInstance(int id) {
     return gInstances[id];
 }
 
+// a pattern-sharded instance forwards every call to its shards (multi.cu); SH(expr) runs at the top of an entry point
+#define SH(id, expr)                                                                         \
+    do {                                                                                     \
+        Instance* p__ = getInstance(id);                                                     \
+        if (p__ != nullptr && p__->shard != nullptr) {                                       \
+            Sharded* sh = static_cast<Sharded*>(p__->shard);                                 \
+            (void)sh;                                                                        \
+            return (expr);                                                                   \
+        }                                                                                    \
+    } while (0)
+
 #define GET_INSTANCE(in, id)                                            \
     Instance* in = getInstance(id);                                     \
     if (in == nullptr) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;      \
+    if (in->shard != nullptr) return BEAGLE_ERROR_NO_IMPLEMENTATION;    \
     if (cudaSetDevice(in->device) != cudaSuccess) return BEAGLE_ERROR_GENERAL;
 
 #define CUDA_OK(expr)                                                                        \
@@ -126,7 +140,9 @@ double* ensurePartials(Instance* in, int idx) {
 bool validRange(int idx, int n) { return idx >= 0 && idx < n; }
 
 void destroyInstance(Instance* in) {
+    if (in->shard != nullptr) { shardedDestroy(in); delete in; return; }
     cudaSetDevice(in->device);
+    exchangeRelease(in);
     if (in->stream) cudaStreamSynchronize(in->stream);
     cudaFree(in->partialsBase); cudaFree(in->states8Base); cudaFree(in->states32Base);
     for (CachedPlan& cp : in->planCache) { if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec); cudaFree(cp.dBlock); }
@@ -144,6 +160,8 @@ void destroyInstance(Instance* in) {
 
 // ---- resources ------------------------------------------------------------------------------
 std::vector<BeagleResource> gResources;
+std::vector<int> gShardDevices;          // devices of the pattern-sharded resource (empty: not offered)
+int gShardResource = -1;                 // its resource number
 std::vector<std::string> gResourceStrings;
 BeagleResourceList gResourceList = {nullptr, 0};
 std::once_flag gResourceOnce;
@@ -164,6 +182,30 @@ void buildResources() {
                  "B200-native walk kernels (sm_100a), double precision",
                  (size_t)(prop.totalGlobalMem >> 20), prop.multiProcessorCount, prop.major, prop.minor);
         gResourceStrings.push_back(buf);
+    }
+    // the engine's own multi-GPU resource (multi.cu): one instance, site patterns sharded over the listed devices.
+    // B200_SHARD_DEVICES="0,1,2,3" overrides the device list (a device may repeat: shards then share it -- test rigs).
+    gShardDevices.clear();
+    if (const char* env = getenv("B200_SHARD_DEVICES")) {
+        for (const char* q = env; *q;) {
+            char* end = nullptr;
+            const long d = strtol(q, &end, 10);
+            if (end == q) break;
+            if (d >= 0 && d < n) gShardDevices.push_back((int)d);
+            q = (*end == ',') ? end + 1 : end;
+        }
+    } else {
+        for (int d = 0; d < n; ++d) gShardDevices.push_back(d);
+    }
+    if (gShardDevices.size() > (size_t)kMaxGroup) gShardDevices.resize(kMaxGroup);
+    if (!gShardDevices.empty()) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "B200 x %zu (pattern-sharded)", gShardDevices.size());
+        gResourceStrings.push_back(buf);
+        snprintf(buf, sizeof buf, "one instance over %zu GPUs | contiguous pattern blocks (Patterns.java:142-169 rule) | "
+                 "per-shard sums added over NVLink inside the root kernel", gShardDevices.size());
+        gResourceStrings.push_back(buf);
+        gShardResource = (int)(gResourceStrings.size() / 2) - 1;
     }
     size_t count = gResourceStrings.size() / 2;
     gResources.resize(count);
@@ -800,6 +842,10 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
 
 }  // namespace
 
+namespace b200 {
+Instance* instanceById(int id) { return getInstance(id); }
+}
+
 // ==============================================================================================
 // exported C ABI
 // ==============================================================================================
@@ -844,6 +890,31 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
             if (resourceList[k] >= 1 && resourceList[k] < rl->length) { resource = resourceList[k]; break; }
     }
     if (resource < 1) return BEAGLE_ERROR_NO_RESOURCE;   // no CUDA device, or only resource 0 requested
+
+    if (resource == gShardResource) {
+        // one instance over several GPUs: the shards are ordinary instances, this id only forwards (multi.cu)
+        Instance* parent = new Instance();
+        parent->resource = resource;
+        parent->device = gShardDevices[0];
+        parent->P = patternCount; parent->S = stateCount; parent->C = categoryCount; parent->tipCount = tipCount;
+        const int g = (int)gShardDevices.size();
+        const int rc = shardedCreate(parent, g, gShardDevices.data(), tipCount, partialsBufferCount, compactBufferCount,
+                                     stateCount, patternCount, eigenBufferCount, matrixBufferCount, categoryCount,
+                                     scaleBufferCount, preferenceFlags, requirementFlags, returnInfo);
+        if (rc != BEAGLE_SUCCESS) { delete parent; return rc; }
+        if (returnInfo != nullptr) {
+            returnInfo->resourceNumber = resource;
+            returnInfo->resourceName = rl->list[resource].name;
+            parent->flags = returnInfo->flags;
+        }
+        std::lock_guard<std::mutex> lock(gMutex);
+        int id = -1;
+        for (size_t k = 0; k < gInstances.size(); ++k) if (gInstances[k] == nullptr) { id = (int)k; break; }
+        if (id < 0) { gInstances.push_back(nullptr); id = (int)gInstances.size() - 1; }
+        gInstances[id] = parent;
+        parent->id = id;
+        return id;
+    }
 
     Instance* in = new Instance();
     in->device = resource - 1;
@@ -892,7 +963,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->eigenReal.assign(std::max(1, in->nEigen), 0);
     in->hEigen.assign((size_t)std::max(1, in->nEigen) * 36, 0.0);
     in->eigenWalk = envInt("B200_EIGEN_WALK", 1);
-    in->tipMode = envInt("B200_TIP_MODE", 0);
+    in->tipMode = envInt("B200_TIP_MODE", 2);
     in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 0);
     in->reorder = envInt("B200_REORDER", 1);
@@ -1026,6 +1097,7 @@ int beagleFinalize(void) {
 }
 
 int beagleSetCPUThreadCount(int instance, int) {
+    SH(instance, BEAGLE_SUCCESS);
     GET_INSTANCE(in, instance);
     (void)in;
     return BEAGLE_SUCCESS;
@@ -1033,6 +1105,7 @@ int beagleSetCPUThreadCount(int instance, int) {
 
 // ---- data upload ------------------------------------------------------------------------------
 int beagleSetTipStates(int instance, int tipIndex, const int* inStates) {
+    SH(instance, shSetTipStates(sh, tipIndex, inStates));
     GET_INSTANCE(in, instance);
     if (!validRange(tipIndex, in->nBuffers) || inStates == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
     std::vector<int> s32(in->Ppad, in->S);
@@ -1056,6 +1129,7 @@ int beagleSetTipStates(int instance, int tipIndex, const int* inStates) {
 }
 
 int beagleGetTipStates(int instance, int tipIndex, int* outStates) {
+    SH(instance, shGetTipStates(sh, tipIndex, outStates));
     GET_INSTANCE(in, instance);
     if (!validRange(tipIndex, in->nBuffers) || in->states32[tipIndex] == nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
     CUDA_OK(cudaMemcpyAsync(outStates, in->states32[tipIndex], sizeof(int) * in->P, cudaMemcpyDeviceToHost, in->stream));
@@ -1087,16 +1161,19 @@ static int setPartialsImpl(Instance* in, int bufferIndex, const double* inPartia
 }
 
 int beagleSetTipPartials(int instance, int tipIndex, const double* inPartials) {
+    SH(instance, shSetPartials(sh, tipIndex, inPartials, false));
     GET_INSTANCE(in, instance);
     return setPartialsImpl(in, tipIndex, inPartials, false);
 }
 
 int beagleSetPartials(int instance, int bufferIndex, const double* inPartials) {
+    SH(instance, shSetPartials(sh, bufferIndex, inPartials, true));
     GET_INSTANCE(in, instance);
     return setPartialsImpl(in, bufferIndex, inPartials, true);
 }
 
 int beagleGetPartials(int instance, int bufferIndex, int scaleIndex, double* outPartials) {
+    SH(instance, shGetPartials(sh, bufferIndex, scaleIndex, outPartials));
     GET_INSTANCE(in, instance);
     if (!validRange(bufferIndex, in->nBuffers) || in->partials[bufferIndex] == nullptr || outPartials == nullptr)
         return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -1123,6 +1200,7 @@ int beagleGetPartials(int instance, int bufferIndex, int scaleIndex, double* out
 
 int beagleSetEigenDecomposition(int instance, int eigenIndex, const double* inEigenVectors,
                                 const double* inInverseEigenVectors, const double* inEigenValues) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleSetEigenDecomposition(c, eigenIndex, inEigenVectors, inInverseEigenVectors, inEigenValues); }));
     GET_INSTANCE(in, instance);
     if (!validRange(eigenIndex, in->nEigen)) return BEAGLE_ERROR_OUT_OF_RANGE;
     const size_t S = in->S, stride = 2 * S * S + 2 * S;
@@ -1150,6 +1228,7 @@ int beagleSetEigenDecomposition(int instance, int eigenIndex, const double* inEi
 }
 
 int beagleSetStateFrequencies(int instance, int stateFrequenciesIndex, const double* inStateFrequencies) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleSetStateFrequencies(c, stateFrequenciesIndex, inStateFrequencies); }));
     GET_INSTANCE(in, instance);
     if (!validRange(stateFrequenciesIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
     std::vector<double> f(in->Sp, 0.0);
@@ -1158,12 +1237,14 @@ int beagleSetStateFrequencies(int instance, int stateFrequenciesIndex, const dou
 }
 
 int beagleSetCategoryWeights(int instance, int categoryWeightsIndex, const double* inCategoryWeights) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleSetCategoryWeights(c, categoryWeightsIndex, inCategoryWeights); }));
     GET_INSTANCE(in, instance);
     if (!validRange(categoryWeightsIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
     return uploadSmall(in, in->dWeights + (size_t)categoryWeightsIndex * in->C, inCategoryWeights, sizeof(double) * in->C);
 }
 
 int beagleSetCategoryRatesWithIndex(int instance, int categoryRatesIndex, const double* inCategoryRates) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleSetCategoryRatesWithIndex(c, categoryRatesIndex, inCategoryRates); }));
     GET_INSTANCE(in, instance);
     if (!validRange(categoryRatesIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
     return uploadSmall(in, in->dRates + (size_t)categoryRatesIndex * in->C, inCategoryRates, sizeof(double) * in->C);
@@ -1174,6 +1255,7 @@ int beagleSetCategoryRates(int instance, const double* inCategoryRates) {
 }
 
 int beagleSetPatternWeights(int instance, const double* inPatternWeights) {
+    SH(instance, shSetPatternWeights(sh, inPatternWeights));
     GET_INSTANCE(in, instance);
     std::vector<double> w(in->Ppad, 0.0);
     memcpy(w.data(), inPatternWeights, sizeof(double) * in->P);
@@ -1183,6 +1265,7 @@ int beagleSetPatternWeights(int instance, const double* inPatternWeights) {
 }
 
 int beagleSetPatternPartitions(int instance, int partitionCount, const int* inPatternPartitions) {
+    SH(instance, BEAGLE_ERROR_NO_IMPLEMENTATION);
     GET_INSTANCE(in, instance);
     if (partitionCount < 1 || partitionCount > 1000) return BEAGLE_ERROR_OUT_OF_RANGE;
     // contiguous, non-decreasing maps only -- what MPDLD:520-533 builds
@@ -1239,6 +1322,7 @@ static int updateMatricesImpl(Instance* in, const int* eigenIndices, int eigenIn
 int beagleUpdateTransitionMatrices(int instance, int eigenIndex, const int* probabilityIndices,
                                    const int* firstDerivativeIndices, const int* secondDerivativeIndices,
                                    const double* edgeLengths, int count) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleUpdateTransitionMatrices(c, eigenIndex, probabilityIndices, firstDerivativeIndices, secondDerivativeIndices, edgeLengths, count); }));
     GET_INSTANCE(in, instance);
     if (firstDerivativeIndices != nullptr || secondDerivativeIndices != nullptr)
         return BEAGLE_ERROR_NO_IMPLEMENTATION;      // derivative matrices: SURVEY.md 8f "next"
@@ -1250,6 +1334,7 @@ int beagleUpdateTransitionMatricesWithMultipleModels(int instance, const int* ei
                                                      const int* firstDerivativeIndices,
                                                      const int* secondDerivativeIndices, const double* edgeLengths,
                                                      int count) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleUpdateTransitionMatricesWithMultipleModels(c, eigenIndices, categoryRateIndices, probabilityIndices, firstDerivativeIndices, secondDerivativeIndices, edgeLengths, count); }));
     GET_INSTANCE(in, instance);
     if (firstDerivativeIndices != nullptr || secondDerivativeIndices != nullptr)
         return BEAGLE_ERROR_NO_IMPLEMENTATION;
@@ -1262,6 +1347,7 @@ static inline size_t matIndex(const Instance* in, int c, int i, int j) {
 }
 
 int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMatrix, double) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleSetTransitionMatrix(c, matrixIndex, inMatrix, 0.0); }));
     GET_INSTANCE(in, instance);
     if (!validRange(matrixIndex, in->nMatrices)) return BEAGLE_ERROR_OUT_OF_RANGE;
     if (in->matCP > 0) in->matEigen[matrixIndex] = -1;        // set directly: no spectrum, matrix-form kernel only
@@ -1294,6 +1380,7 @@ int beagleSetTransitionMatrix(int instance, int matrixIndex, const double* inMat
 }
 
 int beagleGetTransitionMatrix(int instance, int matrixIndex, double* outMatrix) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleGetTransitionMatrix(c, matrixIndex, outMatrix); }));
     GET_INSTANCE(in, instance);
     if (!validRange(matrixIndex, in->nMatrices)) return BEAGLE_ERROR_OUT_OF_RANGE;
     const size_t n = in->matStride;
@@ -1342,14 +1429,17 @@ static int combineMatrices(int instance, const int* firstIndices, const int* sec
 
 int beagleConvolveTransitionMatrices(int instance, const int* firstIndices, const int* secondIndices,
                                      const int* resultIndices, int matrixCount) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleConvolveTransitionMatrices(c, firstIndices, secondIndices, resultIndices, matrixCount); }));
     return combineMatrices(instance, firstIndices, secondIndices, resultIndices, matrixCount, true);
 }
 
 int beagleAddTransitionMatrices(int instance, const int* firstIndices, const int* secondIndices, const int* resultIndices,
                                 int matrixCount) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleAddTransitionMatrices(c, firstIndices, secondIndices, resultIndices, matrixCount); }));
     return combineMatrices(instance, firstIndices, secondIndices, resultIndices, matrixCount, false);
 }
 int beagleTransposeTransitionMatrices(int instance, const int* inputIndices, const int* resultIndices, int matrixCount) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleTransposeTransitionMatrices(c, inputIndices, resultIndices, matrixCount); }));
     GET_INSTANCE(in, instance);
     std::vector<double> m((size_t)in->C * in->S * in->S), t(m.size());
     for (int q = 0; q < matrixCount; ++q) {
@@ -1368,6 +1458,7 @@ int beagleTransposeTransitionMatrices(int instance, const int* inputIndices, con
 // ---- partials ---------------------------------------------------------------------------------
 int beagleUpdatePartials(int instance, const BeagleOperation* operations, int operationCount,
                          int cumulativeScaleIndex) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleUpdatePartials(c, operations, operationCount, cumulativeScaleIndex); }));
     GET_INSTANCE(in, instance);
     if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
     std::vector<HostOp> hops(operationCount);
@@ -1380,6 +1471,7 @@ int beagleUpdatePartials(int instance, const BeagleOperation* operations, int op
 }
 
 int beagleUpdatePartialsByPartition(int instance, const BeagleOperationByPartition* operations, int operationCount) {
+    SH(instance, BEAGLE_ERROR_NO_IMPLEMENTATION);
     GET_INSTANCE(in, instance);
     if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
     std::vector<HostOp> hops(operationCount);
@@ -1393,12 +1485,14 @@ int beagleUpdatePartialsByPartition(int instance, const BeagleOperationByPartiti
 }
 
 int beagleWaitForPartials(int instance, const int*, int) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleWaitForPartials(c, nullptr, 0); }));
     GET_INSTANCE(in, instance);
     CUDA_OK(cudaStreamSynchronize(in->stream));
     return BEAGLE_SUCCESS;
 }
 
 int beagleUpdatePrePartials(int instance, const BeagleOperation* operations, int operationCount, int cumulativeScaleIndex) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleUpdatePrePartials(c, operations, operationCount, cumulativeScaleIndex); }));
     GET_INSTANCE(in, instance);
     if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
     std::vector<HostOp> hops(operationCount);
@@ -1411,6 +1505,7 @@ int beagleUpdatePrePartials(int instance, const BeagleOperation* operations, int
     return planAndLaunch(in, hops, false);
 }
 int beagleUpdatePrePartialsByPartition(int instance, const BeagleOperationByPartition* operations, int operationCount) {
+    SH(instance, BEAGLE_ERROR_NO_IMPLEMENTATION);
     GET_INSTANCE(in, instance);
     if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
     std::vector<HostOp> hops(operationCount);
@@ -1438,12 +1533,14 @@ static int accumulateImpl(Instance* in, const int* scaleIndices, int count, int 
 }
 
 int beagleAccumulateScaleFactors(int instance, const int* scaleIndices, int count, int cumulativeScaleIndex) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleAccumulateScaleFactors(c, scaleIndices, count, cumulativeScaleIndex); }));
     GET_INSTANCE(in, instance);
     return accumulateImpl(in, scaleIndices, count, cumulativeScaleIndex, 1.0, 0, in->P);
 }
 
 int beagleAccumulateScaleFactorsByPartition(int instance, const int* scaleIndices, int count,
                                             int cumulativeScaleIndex, int partitionIndex) {
+    SH(instance, BEAGLE_ERROR_NO_IMPLEMENTATION);
     GET_INSTANCE(in, instance);
     if (!validRange(partitionIndex, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
     return accumulateImpl(in, scaleIndices, count, cumulativeScaleIndex, 1.0, in->partBegin[partitionIndex],
@@ -1451,12 +1548,14 @@ int beagleAccumulateScaleFactorsByPartition(int instance, const int* scaleIndice
 }
 
 int beagleRemoveScaleFactors(int instance, const int* scaleIndices, int count, int cumulativeScaleIndex) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleRemoveScaleFactors(c, scaleIndices, count, cumulativeScaleIndex); }));
     GET_INSTANCE(in, instance);
     return accumulateImpl(in, scaleIndices, count, cumulativeScaleIndex, -1.0, 0, in->P);
 }
 
 int beagleRemoveScaleFactorsByPartition(int instance, const int* scaleIndices, int count, int cumulativeScaleIndex,
                                         int partitionIndex) {
+    SH(instance, BEAGLE_ERROR_NO_IMPLEMENTATION);
     GET_INSTANCE(in, instance);
     if (!validRange(partitionIndex, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
     return accumulateImpl(in, scaleIndices, count, cumulativeScaleIndex, -1.0, in->partBegin[partitionIndex],
@@ -1464,6 +1563,7 @@ int beagleRemoveScaleFactorsByPartition(int instance, const int* scaleIndices, i
 }
 
 int beagleResetScaleFactors(int instance, int cumulativeScaleIndex) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleResetScaleFactors(c, cumulativeScaleIndex); }));
     GET_INSTANCE(in, instance);
     if (!validRange(cumulativeScaleIndex, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
     CUDA_OK(cudaMemsetAsync(in->dScale + (size_t)cumulativeScaleIndex * in->Ppad, 0, sizeof(double) * in->Ppad, in->stream));
@@ -1472,6 +1572,7 @@ int beagleResetScaleFactors(int instance, int cumulativeScaleIndex) {
 }
 
 int beagleResetScaleFactorsByPartition(int instance, int cumulativeScaleIndex, int partitionIndex) {
+    SH(instance, BEAGLE_ERROR_NO_IMPLEMENTATION);
     GET_INSTANCE(in, instance);
     if (!validRange(cumulativeScaleIndex, in->nScale) || !validRange(partitionIndex, in->partitionCount))
         return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -1483,6 +1584,7 @@ int beagleResetScaleFactorsByPartition(int instance, int cumulativeScaleIndex, i
 }
 
 int beagleCopyScaleFactors(int instance, int destScalingIndex, int srcScalingIndex) {
+    SH(instance, shBroadcast(sh, [&](int c) { return beagleCopyScaleFactors(c, destScalingIndex, srcScalingIndex); }));
     GET_INSTANCE(in, instance);
     if (!validRange(destScalingIndex, in->nScale) || !validRange(srcScalingIndex, in->nScale))
         return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -1493,6 +1595,7 @@ int beagleCopyScaleFactors(int instance, int destScalingIndex, int srcScalingInd
 }
 
 int beagleGetScaleFactors(int instance, int srcScalingIndex, double* outScaleFactors) {
+    SH(instance, shGetPerPattern(sh, outScaleFactors, [&](int c, double* o) { return beagleGetScaleFactors(c, srcScalingIndex, o); }));
     GET_INSTANCE(in, instance);
     if (!validRange(srcScalingIndex, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
     CUDA_OK(cudaMemcpyAsync(outScaleFactors, in->dScale + (size_t)srcScalingIndex * in->Ppad, sizeof(double) * in->P,
@@ -1502,6 +1605,7 @@ int beagleGetScaleFactors(int instance, int srcScalingIndex, double* outScaleFac
 }
 
 int beagleGetLogScaleFactors(int instance, int srcScalingIndex, double* outLogScaleFactors) {
+    SH(instance, shGetPerPattern(sh, outLogScaleFactors, [&](int c, double* o) { return beagleGetLogScaleFactors(c, srcScalingIndex, o); }));
     int rc = beagleGetScaleFactors(instance, srcScalingIndex, outLogScaleFactors);
     if (rc != BEAGLE_SUCCESS) return rc;
     Instance* in = getInstance(instance);
@@ -1512,24 +1616,31 @@ int beagleGetLogScaleFactors(int instance, int srcScalingIndex, double* outLogSc
 }
 
 // ---- root -------------------------------------------------------------------------------------
-static int rootLaunch(Instance* in, int buffer, int wIdx, int fIdx, int cum, int pBegin, int pEnd, double* dOutSlot) {
+static int rootLaunch(Instance* in, int buffer, int wIdx, int fIdx, int cum, int pBegin, int pEnd, double* dOutSlot,
+                      bool joint = false) {
     if (!validRange(buffer, in->nBuffers) || in->partials[buffer] == nullptr || !validRange(wIdx, in->nSets) ||
         !validRange(fIdx, in->nSets))
         return BEAGLE_ERROR_OUT_OF_RANGE;
     if (cum != BEAGLE_OP_NONE && !validRange(cum, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
     TimedScope ts(in, T_ROOT);
+    const Exchange* ex = nullptr;
+    if (joint && in->exchangeOn) {          // member of a reduce group: the kernel adds the other shards' sums (Exchange)
+        in->exchange.seq++;
+        ex = &in->exchange;
+    }
     CUDA_OK(launchRoot(in, in->partials[buffer], in->dWeights + (size_t)wIdx * in->C, in->dFreqs + (size_t)fIdx * in->Sp,
-                       cum == BEAGLE_OP_NONE ? nullptr : in->dScale + (size_t)cum * in->Ppad, pBegin, pEnd, dOutSlot));
+                       cum == BEAGLE_OP_NONE ? nullptr : in->dScale + (size_t)cum * in->Ppad, pBegin, pEnd, dOutSlot, ex));
     return BEAGLE_SUCCESS;
 }
 
 int beagleCalculateRootLogLikelihoods(int instance, const int* bufferIndices, const int* categoryWeightsIndices,
                                       const int* stateFrequenciesIndices, const int* cumulativeScaleIndices,
                                       int count, double* outSumLogLikelihood) {
+    SH(instance, shRoot(sh, bufferIndices, categoryWeightsIndices, stateFrequenciesIndices, cumulativeScaleIndices, count, outSumLogLikelihood));
     GET_INSTANCE(in, instance);
     if (count != 1) return BEAGLE_ERROR_NO_IMPLEMENTATION;   // BEAST always passes 1 (BDLD:934-935)
     int rc = rootLaunch(in, bufferIndices[0], categoryWeightsIndices[0], stateFrequenciesIndices[0],
-                        cumulativeScaleIndices[0], 0, in->P, in->dOut);
+                        cumulativeScaleIndices[0], 0, in->P, in->dOut, true);
     if (rc != BEAGLE_SUCCESS) return rc;
     CUDA_OK(cudaMemcpyAsync(in->hOut, in->dOut, sizeof(double), cudaMemcpyDeviceToHost, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
@@ -1543,6 +1654,7 @@ int beagleCalculateRootLogLikelihoodsByPartition(int instance, const int* buffer
                                                  const int* cumulativeScaleIndices, const int* partitionIndices,
                                                  int partitionCount, int count,
                                                  double* outSumLogLikelihoodByPartition, double* outSumLogLikelihood) {
+    SH(instance, BEAGLE_ERROR_NO_IMPLEMENTATION);
     GET_INSTANCE(in, instance);
     if (count != 1) return BEAGLE_ERROR_NO_IMPLEMENTATION;
     if (partitionCount < 1 || partitionCount > 1000) return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -1562,6 +1674,7 @@ int beagleCalculateRootLogLikelihoodsByPartition(int instance, const int* buffer
 }
 
 int beagleGetSiteLogLikelihoods(int instance, double* outLogLikelihoods) {
+    SH(instance, shGetPerPattern(sh, outLogLikelihoods, [&](int c, double* o) { return beagleGetSiteLogLikelihoods(c, o); }));
     GET_INSTANCE(in, instance);
     CUDA_OK(cudaMemcpyAsync(outLogLikelihoods, in->dSite, sizeof(double) * in->P, cudaMemcpyDeviceToHost, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
@@ -1585,6 +1698,7 @@ static cudaError_t ensureScratch(Instance* in, size_t doubles) {
 int beagleCalculateEdgeDerivatives(int instance, const int* postBufferIndices, const int* preBufferIndices,
                                    const int* derivativeMatrixIndices, const int* categoryWeightsIndices, int count,
                                    double* outDerivatives, double* outSumDerivatives, double* outSumSquaredDerivatives) {
+    SH(instance, shEdgeDerivatives(sh, postBufferIndices, preBufferIndices, derivativeMatrixIndices, categoryWeightsIndices, count, outDerivatives, outSumDerivatives, outSumSquaredDerivatives));
     GET_INSTANCE(in, instance);
     if (count <= 0) return BEAGLE_SUCCESS;
     if (!validRange(categoryWeightsIndices[0], in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -1632,6 +1746,7 @@ int beagleCalculateCrossProductDerivative(int instance, const int* postBufferInd
                                           const int* categoryRatesIndices, const int* categoryWeightsIndices,
                                           const double* edgeLengths, int count, double* outSumDerivatives,
                                           double* outSumSquaredDerivatives) {
+    SH(instance, shCrossProducts(sh, postBufferIndices, preBufferIndices, categoryRatesIndices, categoryWeightsIndices, edgeLengths, count, outSumDerivatives, outSumSquaredDerivatives));
     GET_INSTANCE(in, instance);
     if (outSumSquaredDerivatives != nullptr) return BEAGLE_ERROR_NO_IMPLEMENTATION;   // BEAST passes null (:161,:175)
     if (count <= 0) return BEAGLE_SUCCESS;
@@ -1696,6 +1811,7 @@ int b200DebugPlan(const int* operations, int operationCount, int bufferCount, in
 
 // ---- engine extensions ------------------------------------------------------------------------
 int b200SetKernelTiming(int instance, int enable) {
+    SH(instance, shBroadcast(sh, [&](int c) { return b200SetKernelTiming(c, enable); }));
     GET_INSTANCE(in, instance);
     CUDA_OK(cudaStreamSynchronize(in->stream));
     for (int c = 0; c < T_CLASSES; ++c) {
@@ -1844,6 +1960,18 @@ BeagleBenchmarkedResourceList* beagleGetBenchmarkedResourceList(
     return list.length > 0 ? &list : nullptr;
 }
 
+// devices of the pattern-sharded resource for instances created from now on (default: every GPU; a device may repeat)
+int b200SetShardDevices(const int* devices, int count) {
+    beagleGetResourceList();
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (count < 1 || count > kMaxGroup || gShardResource < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+    for (int k = 0; k < count; ++k) if (devices[k] < 0 || devices[k] >= n) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::lock_guard<std::mutex> lock(gMutex);
+    gShardDevices.assign(devices, devices + count);
+    return BEAGLE_SUCCESS;
+}
+
 void* b200HostAlloc(long bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -1856,7 +1984,7 @@ int b200RootLogLikelihoodDevice(int instance, int bufferIndex, int categoryWeigh
                                 int cumulativeScaleIndex, void** outDevicePointer, void** outStream) {
     GET_INSTANCE(in, instance);
     int rc = rootLaunch(in, bufferIndex, categoryWeightsIndex, stateFrequenciesIndex, cumulativeScaleIndex, 0, in->P,
-                        in->dOut);
+                        in->dOut, true);
     if (rc != BEAGLE_SUCCESS) return rc;
     if (outDevicePointer) *outDevicePointer = in->dOut;
     if (outStream) *outStream = in->stream;

@@ -78,6 +78,22 @@ struct CachedPlan {
 
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
 
+// ---- cross-GPU sum of the per-shard log-likelihoods, fused into k_root (no NCCL launch, no host in the loop) -------------
+// Every member of a reduce group owns [2 banks][size] slots in ITS device memory; all members map all members' slots
+// (peer access inside a process, CUDA IPC across processes).  The finishing block of k_root stores {local sum, sequence
+// number} into slot [bank][rank] of EVERY member over NVLink (value, system fence, then the sequence number), then spins
+// on its own device's slots until all `size` entries carry this evaluation's sequence number and adds them in rank
+// order: every member ends up with the same, deterministic joint value.  Two banks suffice: a member can only reach
+// evaluation k+2 after it has seen every peer's k+1, which each peer wrote after it finished reading bank k.
+constexpr int kMaxGroup = 16;
+struct ExchangeSlot { double value; unsigned long long seq; };
+struct Exchange {
+    int rank = 0, size = 1;
+    unsigned long long seq = 0;              // sequence number of THIS evaluation (host-incremented per root launch)
+    long long timeoutCycles = 0;             // spin budget (SM clocks) before giving up with NaN
+    ExchangeSlot* peers[kMaxGroup] = {};     // member q's slot array as mapped on this device (peers[rank] = own)
+};
+
 struct Instance {
     int id = -1, device = 0, resource = 0;
     int tipCount = 0, nPartials = 0, nCompact = 0, S = 0, P = 0, nEigen = 0, nMatrices = 0, C = 0, nScale = 0;
@@ -111,7 +127,7 @@ struct Instance {
     std::vector<char> eigenReal;
     std::vector<double> hEigen;               // [nEigen][32]: V | V^-1 padded to 4 x 4 (host copy, by value into the launch)
     int eigenWalk = 1;                        // B200_EIGEN_WALK: 0 = always the matrix-form kernel
-    int tipMode = 0;                          // B200_TIP_MODE: eigen-form walk, compact tips by contraction (0) or P column (1)
+    int tipMode = 2;                          // B200_TIP_MODE: compact tips by contraction (0), P column from global (1), shared-memory column table (2)
     double* dRates = nullptr;                 // [nSets][C]
     double* dWeights = nullptr;               // [nSets][C]
     double* dFreqs = nullptr;                 // [nSets][Sp]
@@ -140,6 +156,13 @@ struct Instance {
     size_t stageSize = 0, stagePos = 0;
     double* hOut = nullptr;                   // pinned result landing zone
 
+    void* shard = nullptr;                    // non-null: this id is a pattern-sharded instance over several GPUs (multi.cu)
+    // reduce group (b200Exchange*): set up once, used by every single-root launch from then on
+    Exchange exchange;
+    ExchangeSlot* dSlots = nullptr;           // own slots [2][size]
+    std::vector<void*> ipcOpened;             // peers' slot arrays opened through CUDA IPC (closed at finalize)
+    bool exchangeOn = false;
+
     // kernel timing (bench.py roofline): events around every launch of a class
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[T_CLASSES];
@@ -167,6 +190,15 @@ struct Instance {
     int phaseT = 0;              // max ops per subtree walk (0 = automatic)
 };
 
+// ---- multi-GPU layer (multi.cu) --------------------------------------------------------------------
+struct Sharded;
+Instance* instanceById(int id);               // api.cu: nullptr when the id is free
+void exchangeRelease(Instance* in);
+int shardedCreate(Instance* parent, int g, const int* devices, int tipCount, int partialsBufferCount, int compactBufferCount,
+                  int stateCount, int patternCount, int eigenBufferCount, int matrixBufferCount, int categoryCount,
+                  int scaleBufferCount, long preferenceFlags, long requirementFlags, void* details /* BeagleInstanceDetails* */);
+void shardedDestroy(Instance* parent);
+
 // ---- kernel launchers (kernels.cu) -----------------------------------------------------------
 cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const int* dEigenIdx,
                                      const int* dRateSet, const double* dLengths, int count);
@@ -186,8 +218,9 @@ int compressSitePatterns(int device, int taxa, int sites, const int* hStates, in
 int crossProductBlocks(const Instance* in, int count);
 cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, const double* rates,
                                 const double* weights, double* scratch);
+// exchange: non-null = add the other members' sums inside the kernel (dOutSlot[0] = joint value, dOutSlot[1] = local)
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
-                       const double* cumScale, int pBegin, int pEnd, double* dOutSlot);
+                       const double* cumScale, int pBegin, int pEnd, double* dOutSlot, const Exchange* exchange = nullptr);
 cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,
                                   int pBegin, int pEnd);
 cudaError_t launchRescalePartialsForGet(Instance* in, double* tmp, const double* cum);

@@ -17,6 +17,7 @@
 #include "engine.h"
 #include "walk4.cuh"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace b200 {
@@ -1769,11 +1770,20 @@ cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, 
 // ---------------------------------------------------------------------------------------------
 // site[p] = log(sum_i pi_i (sum_c w_c root[c,p,i])) + cum[p]   (GeneralLikelihoodCore.java:358-408)
 // out     = sum_p weight[p] site[p], deterministic two-level tree (fixed shape => reproducible).
+__device__ __forceinline__ void storeSys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long loadSys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(256)
 k_root(const double* __restrict__ root, const double* __restrict__ weights, const double* __restrict__ freqs,
        const double* __restrict__ cumScale, const double* __restrict__ patternWeights, int S, int Sp, int C,
        int Ppad, int pBegin, int pEnd, double* __restrict__ site, double* __restrict__ blockSums,
-       unsigned int* __restrict__ counter, double* __restrict__ out) {
+       unsigned int* __restrict__ counter, double* __restrict__ out, const Exchange ex) {
     __shared__ double red[256];
     __shared__ bool last;
     const int p = pBegin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -1813,18 +1823,50 @@ k_root(const double* __restrict__ root, const double* __restrict__ weights, cons
             if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
             __syncthreads();
         }
-        if (threadIdx.x == 0) { *out = red[0]; *counter = 0u; }
+        if (ex.size <= 1) {
+            if (threadIdx.x == 0) { *out = red[0]; *counter = 0u; }
+            return;
+        }
+        // ---- reduce group: this shard's sum goes to every member over NVLink, theirs are added here (engine.h, Exchange)
+        __shared__ double theirs[kMaxGroup];
+        const double mine = red[0];
+        const int bank = (int)(ex.seq & 1ull);
+        if (threadIdx.x < ex.size) {
+            const int q = threadIdx.x;
+            ExchangeSlot* dst = ex.peers[q] + bank * ex.size + ex.rank;
+            dst->value = mine;
+            __threadfence_system();
+            storeSys(&dst->seq, ex.seq);
+            const ExchangeSlot* src = ex.peers[ex.rank] + bank * ex.size + q;     // own device's copy of member q's entry
+            const long long t0 = clock64();
+            bool ok = true;
+            while (loadSys(&src->seq) != ex.seq) {
+                if (clock64() - t0 > ex.timeoutCycles) { ok = false; break; }
+                __nanosleep(64);
+            }
+            theirs[q] = ok ? src->value : __longlong_as_double(0x7ff8000000000000ll);   // a peer never arrived: NaN
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double joint = 0.0;
+            for (int q = 0; q < ex.size; ++q) joint += theirs[q];                 // rank order: identical on every member
+            out[0] = joint;
+            out[1] = mine;
+            *counter = 0u;
+        }
     }
 }
 
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
-                       const double* cumScale, int pBegin, int pEnd, double* dOutSlot) {
+                       const double* cumScale, int pBegin, int pEnd, double* dOutSlot, const Exchange* exchange) {
     int n = pEnd - pBegin;
-    if (n <= 0) return cudaMemsetAsync(dOutSlot, 0, sizeof(double), in->stream);
-    int blocks = (n + 255) / 256;
+    Exchange ex;                       // size 1: no exchange
+    if (exchange != nullptr) ex = *exchange;
+    if (n <= 0 && ex.size <= 1) return cudaMemsetAsync(dOutSlot, 0, sizeof(double), in->stream);
+    int blocks = std::max(1, (n + 255) / 256);       // an empty shard still takes part in the exchange (sum 0)
     k_root<<<blocks, 256, 0, in->stream>>>(root, weights, freqs, cumScale, in->dPatternWeights, in->S, in->Sp,
                                            in->C, in->Ppad, pBegin, pEnd, in->dSite, in->dBlockSums,
-                                           in->dCounter, dOutSlot);
+                                           in->dCounter, dOutSlot, ex);
     return cudaGetLastError();
 }
 

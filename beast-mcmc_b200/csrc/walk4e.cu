@@ -31,12 +31,55 @@ namespace {
 // TIP = 0: a compact-tip child goes through the same contraction with a one-hot x (no memory traffic, no extra code path);
 // TIP = 1: its value is column s of the stored P matrix (one 32-B load per pattern, no arithmetic) -- the LSU / FP64
 //          trade-off is measured, not guessed (B200_TIP_MODE)
+//          TIP = 2: the columns of P for the five possible tip symbols (4 states + gap) of all categories are staged once per
+//          (op, child) in a per-warp shared-memory table by a handful of lanes; every pattern then picks its 32-B column
+//          with two LDS.128 -- no FP64 work, no dependent global load (the default)
+__device__ __forceinline__ double absBits(double v) {       // |v| on the integer pipe (the FP64 pipe is the busy one here)
+    return __hiloint2double(__double2hiint(v) & 0x7fffffff, __double2loint(v));
+}
+
 template <int CP, int R, bool ALIGNED, bool FIRST, int TIP>
 __device__ __forceinline__ void childTermE(const WalkArgs& A, const double (&Vi)[16], int child, int matIdx, bool fromRegisters,
-                                           int cc, size_t off0, int p0, bool catValid, int pBegin, int pEnd, double (&d)[R][4]) {
+                                           int cc, size_t off0, int p0, bool catValid, int pBegin, int pEnd, double (&d)[R][4],
+                                           double* tab) {
     constexpr int G = 32 / CP;
     const int S = A.S;
     const bool tip = child < 0;
+    if (TIP == 2 && tip) {
+        const int lane = threadIdx.x & 31;
+        const uint8_t* t = A.states + (size_t)(-child - 1) * A.Ppad;
+        int s[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r * G;
+            s[r] = (ALIGNED || (catValid && p >= pBegin && p < pEnd)) ? (int)__ldg(t + p) : 4;
+        }
+        // table [CP][5][4]: column s of P_c (the tip's contribution when it shows state s), s = 4 (and s >= S): all ones
+        const double* m = A.mats + (size_t)matIdx * A.matStride;
+        __syncwarp();                                              // the previous table of this slot is no longer read
+#pragma unroll
+        for (int q = lane; q < 5 * CP; q += 32) {
+            const int c = q / 5, sym = q - 5 * c;
+            double v[4];
+            if (sym < S && sym < 4 && c < A.C) ldg256_ro(m + (sym * CP + c) * 4, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = (i < S) ? 1.0 : 0.0;
+            }
+            double2* dst = reinterpret_cast<double2*>(tab + q * 4);
+            dst[0] = make_double2(v[0], v[1]);
+            dst[1] = make_double2(v[2], v[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double2* col = reinterpret_cast<const double2*>(tab + (cc * 5 + min(s[r], 4)) * 4);
+            const double2 lo = col[0], hi = col[1];
+            if (FIRST) { d[r][0] = lo.x; d[r][1] = lo.y; d[r][2] = hi.x; d[r][3] = hi.y; }
+            else { d[r][0] *= lo.x; d[r][1] *= lo.y; d[r][2] *= hi.x; d[r][3] *= hi.y; }
+        }
+        return;
+    }
     if (TIP == 1 && tip) {
         const uint8_t* t = A.states + (size_t)(-child - 1) * A.Ppad;
         const double* m = A.mats + (size_t)matIdx * A.matStride + cc * 4;
@@ -82,7 +125,7 @@ __device__ __forceinline__ void childTermE(const WalkArgs& A, const double (&Vi)
             u[k] = (Vi[4 * k] * x[0] + Vi[4 * k + 1] * x[1] + Vi[4 * k + 2] * x[2] + Vi[4 * k + 3] * x[3]) * e[k];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            y[i] = fabs(A.V[4 * i] * u[0] + A.V[4 * i + 1] * u[1] + A.V[4 * i + 2] * u[2] + A.V[4 * i + 3] * u[3]);
+            y[i] = absBits(A.V[4 * i] * u[0] + A.V[4 * i + 1] * u[1] + A.V[4 * i + 2] * u[2] + A.V[4 * i + 3] * u[3]);
         if (tip && s >= S) {                                       // gap / unknown: every state is compatible
 #pragma unroll
             for (int i = 0; i < 4; ++i) y[i] = (i < S) ? 1.0 : 0.0;
@@ -106,6 +149,10 @@ k_walk4e(const WalkArgs A) {
     const int cc = catValid ? c : 0;
     const size_t off0 = ((size_t)cc * A.Ppad + p0) * 4;
     const int last = range.y - 1;
+    // per-warp tip tables (TIP == 2): [child slot][CP][5][4] doubles
+    __shared__ __align__(16) double tipTab[TIP == 2 ? 4 * 2 * CP * 20 : 2];
+    double* tab1 = tipTab + (TIP == 2 ? ((threadIdx.x >> 5) * 2) * CP * 20 : 0);
+    double* tab2 = tab1 + (TIP == 2 ? CP * 20 : 0);
 
     // V^-1 in vector registers (the tip selects and the first contraction read it), V stays in the constant bank: both in
     // uniform registers do not fit (64 > 63) and ptxas would spill.  The asm keeps ptxas from folding the copy back.
@@ -132,15 +179,18 @@ k_walk4e(const WalkArgs A) {
                 const double* xg = A.partials + (size_t)((pf >> 1) - 1) * A.stride + off0;
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    if (p0 + r * G < A.Ppad) prefetchL1(xg + (size_t)r * G * 4);
+                    if (ALIGNED || p0 + r * G < A.Ppad) prefetchL1(xg + (size_t)r * G * 4);
             }
         }
         if (lane < 2) {
             const int mi = lane == 0 ? cur.pfM1 : cur.pfM2;
             if (mi >= 0) prefetchL1(A.evecs + (size_t)mi * CP * 4);            // all categories of a branch: one 128-B line
+        } else if (TIP != 0 && lane >= 8 && lane < 16) {
+            const int mi = lane < 12 ? cur.pfM1 : cur.pfM2;                     // matrix rows, should a child be a compact tip
+            if (mi >= 0) prefetchL1(A.mats + (size_t)mi * A.matStride + (lane & 3) * 4 * CP);
         }
-        childTermE<CP, R, ALIGNED, true, TIP>(A, Vi, cur.c1, cur.m1, (cur.pad_ & 2) != 0, cc, off0, p0, catValid, cur.pBegin, cur.pEnd, d);
-        childTermE<CP, R, ALIGNED, false, TIP>(A, Vi, cur.c2, cur.m2, false, cc, off0, p0, catValid, cur.pBegin, cur.pEnd, d);
+        childTermE<CP, R, ALIGNED, true, TIP>(A, Vi, cur.c1, cur.m1, (cur.pad_ & 2) != 0, cc, off0, p0, catValid, cur.pBegin, cur.pEnd, d, tab1);
+        childTermE<CP, R, ALIGNED, false, TIP>(A, Vi, cur.c2, cur.m2, false, cc, off0, p0, catValid, cur.pBegin, cur.pEnd, d, tab2);
         if (R != 1) nxt = loadOp(A.ops + min(k + 1, last));
         double* dg = A.partials + (size_t)cur.dest * A.stride + off0;
 #pragma unroll
@@ -176,25 +226,33 @@ cudaError_t launchK(Instance* in, const WalkArgs& A, dim3 grid) {
     return cudaGetLastError();
 }
 
-// shipped configuration per category count: R in {1, 4} x {aligned, windows}; CP = 4 (the Gamma-4 workloads the metric is
-// quoted on) additionally carries the tuning space behind B200_WALK_R / B200_WALK_MINB / B200_TIP_MODE
+// shipped configuration per category count: R in {1, 4} x {aligned, windows}, tips through the shared-memory column table
+// (CP <= 8) or the contraction; CP = 4 (the Gamma-4 workloads the metric is quoted on) additionally carries the tuning space
+// behind B200_WALK_R / B200_WALK_MINB / B200_TIP_MODE
 template <int CP, int R>
 cudaError_t launchR(Instance* in, WalkArgs& A, int nSubs, int maxWindow, bool aligned) {
     constexpr int G = 32 / CP;
+    constexpr int TIPD = CP <= 8 ? 2 : 0;
     const int warps = (maxWindow + G * R - 1) / (G * R);
     dim3 grid((warps + 3) / 4, nSubs);
-    if (!aligned) return launchK<CP, R, false, 4, 0>(in, A, grid);
+    // predicate-free only when a warp's G*R patterns can never straddle the end of the padded pattern axis
+    if (!aligned || in->Ppad % (G * R) != 0) return launchK<CP, R, false, 4, TIPD>(in, A, grid);
     if constexpr (CP == 4 && R >= 2) {
         const int minb = in->walkMinBlocks, tip = in->tipMode;
+        if (tip == 0) {
+            if (minb >= 5) return launchK<CP, R, true, 5, 0>(in, A, grid);
+            if (minb == 3) return launchK<CP, R, true, 3, 0>(in, A, grid);
+            return launchK<CP, R, true, 4, 0>(in, A, grid);
+        }
         if (tip == 1) {
             if (minb >= 5) return launchK<CP, R, true, 5, 1>(in, A, grid);
-            if (minb == 3) return launchK<CP, R, true, 3, 1>(in, A, grid);
             return launchK<CP, R, true, 4, 1>(in, A, grid);
         }
-        if (minb >= 5) return launchK<CP, R, true, 5, 0>(in, A, grid);
-        if (minb == 3) return launchK<CP, R, true, 3, 0>(in, A, grid);
+        if (minb >= 6) return launchK<CP, R, true, 6, 2>(in, A, grid);
+        if (minb == 5) return launchK<CP, R, true, 5, 2>(in, A, grid);
+        if (minb == 3) return launchK<CP, R, true, 3, 2>(in, A, grid);
     }
-    return launchK<CP, R, true, 4, 0>(in, A, grid);
+    return launchK<CP, R, true, 4, TIPD>(in, A, grid);
 }
 
 template <int CP>

@@ -324,6 +324,27 @@ BEAGLE_DLLEXPORT int b200RootLogLikelihoodDevice(int instance, int bufferIndex, 
                                                  int stateFrequenciesIndex, int cumulativeScaleIndex,
                                                  void** outDevicePointer, void** outStream);
 
+/* ---- multi-GPU -----------------------------------------------------------------------------------
+ * Mode B, one instance over several GPUs: beagleGetResourceList() ends with a resource "B200 x N (pattern-sharded)" on
+ * boxes with >= 2 GPUs; an instance created on it splits its patterns into contiguous blocks (the rule of BEAST's own
+ * -beagle_instances split, src/dr/evolution/alignment/Patterns.java:142-169) over the GPUs and behaves like any other
+ * instance -- beagleCalculateRootLogLikelihoods returns the joint value (CompoundLikelihood.java:214-219 sums the same
+ * shards on the Java side in mode A).  B200_SHARD_DEVICES="0,1,..." (environment) overrides the device list.
+ *
+ * Reduce groups, for callers that keep one instance per GPU themselves (mode A inside one JVM, or one process per GPU):
+ * once connected, every beagleCalculateRootLogLikelihoods / b200RootLogLikelihoodDevice of a member returns the SUM over
+ * all members -- the finishing block of the root kernel stores the shard's sum into every member's device memory over
+ * NVLink and adds what the others stored (no NCCL call, no host arithmetic).  All members must issue the same number of
+ * root evaluations.
+ *   same process : b200ExchangeConnectLocal(instances, count)          (peer mappings)
+ *   one process per GPU: b200ExchangeCreate(instance, rank, size, handle64) on every rank, exchange the 64-byte handles by
+ *                  any means (bench.py: torch.distributed all_gather at set-up), then b200ExchangeConnect(instance,
+ *                  all size*64 bytes in rank order)                    (CUDA IPC mappings) */
+BEAGLE_DLLEXPORT int b200SetShardDevices(const int* devices, int count);   /* device list of the sharded resource from now on */
+BEAGLE_DLLEXPORT int b200ExchangeConnectLocal(const int* instances, int count);
+BEAGLE_DLLEXPORT int b200ExchangeCreate(int instance, int rank, int size, void* outIpcHandle64);
+BEAGLE_DLLEXPORT int b200ExchangeConnect(int instance, const void* allIpcHandles64);
+
 /* The step before the path: SitePatterns.addPatterns with CompressionType.UNIQUE_ONLY
  * (src/dr/evolution/alignment/SitePatterns.java:226-372) on the GPU.  inStates is [taxon][site] (the int state codes
  * SiteList.getSitePattern yields, any values); results: outSitePatternIndices[site], outPatterns [taxon][*outPatternCount]

@@ -413,8 +413,11 @@ def test_full_size_configs_match_c_port(name):
     print(f"{name}: root rel.err {_rel(vg, vc):.2e}; site log-likelihoods max rel.err {err.max():.2e}, "
           f"99.9th percentile {np.quantile(err, 0.999):.2e}")
     assert err.max() <= 5e-9 and np.quantile(err, 0.99) <= 1e-10, (err.max(), np.quantile(err, 0.99))
+    # rescaled partials inherit the same effect (a cherry with t ~ 1e-9 whose tips differ has ALL its entries ~ q t before
+    # the division by their maximum): 1e-6 there, 1e-8 on the codon tree with ordinary branch lengths
+    rtol = 1e-6 if name.startswith("makona") else 1e-8
     for a, b, n in zip(pg, pc, nodes):
-        assert np.allclose(a, b, rtol=1e-8, atol=1e-13 * b.max()), n
+        assert np.allclose(a, b, rtol=rtol, atol=1e-13 * b.max()), (n, float(np.max(np.abs(a - b) / (np.abs(b) + 1e-13 * b.max()))))
 
 
 # ---- two devices from two threads -----------------------------------------------------------------------------------------
