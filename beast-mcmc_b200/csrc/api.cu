@@ -1648,6 +1648,27 @@ int beagleCalculateRootLogLikelihoods(int instance, const int* bufferIndices, co
     return std::isnan(in->hOut[0]) ? BEAGLE_ERROR_FLOATING_POINT : BEAGLE_SUCCESS;
 }
 
+// launches of a *ByPartition root call: one k_root per listed partition into dOut[0..n); a member of a reduce group
+// then adds the members' totals in one more tiny launch (dOut[n] = joint, dOut[n+1] = this member's total)
+static int rootByPartitionLaunch(Instance* in, const int* bufferIndices, const int* categoryWeightsIndices,
+                                 const int* stateFrequenciesIndices, const int* cumulativeScaleIndices,
+                                 const int* partitionIndices, int partitionCount) {
+    if (partitionCount < 1 || partitionCount > 1000) return BEAGLE_ERROR_OUT_OF_RANGE;
+    for (int k = 0; k < partitionCount; ++k) {
+        int part = partitionIndices[k];
+        if (!validRange(part, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        int rc = rootLaunch(in, bufferIndices[k], categoryWeightsIndices[k], stateFrequenciesIndices[k],
+                            cumulativeScaleIndices[k], in->partBegin[part], in->partEnd[part], in->dOut + k);
+        if (rc != BEAGLE_SUCCESS) return rc;
+    }
+    if (in->exchangeOn) {
+        in->exchange.seq++;
+        TimedScope ts(in, T_ROOT);
+        CUDA_OK(launchExchangeSum(in, in->dOut, partitionCount, in->dOut + partitionCount, &in->exchange));
+    }
+    return BEAGLE_SUCCESS;
+}
+
 int beagleCalculateRootLogLikelihoodsByPartition(int instance, const int* bufferIndices,
                                                  const int* categoryWeightsIndices,
                                                  const int* stateFrequenciesIndices,
@@ -1657,18 +1678,15 @@ int beagleCalculateRootLogLikelihoodsByPartition(int instance, const int* buffer
     SH(instance, BEAGLE_ERROR_NO_IMPLEMENTATION);
     GET_INSTANCE(in, instance);
     if (count != 1) return BEAGLE_ERROR_NO_IMPLEMENTATION;
-    if (partitionCount < 1 || partitionCount > 1000) return BEAGLE_ERROR_OUT_OF_RANGE;
-    for (int k = 0; k < partitionCount; ++k) {
-        int part = partitionIndices[k];
-        if (!validRange(part, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
-        int rc = rootLaunch(in, bufferIndices[k], categoryWeightsIndices[k], stateFrequenciesIndices[k],
-                            cumulativeScaleIndices[k], in->partBegin[part], in->partEnd[part], in->dOut + k);
-        if (rc != BEAGLE_SUCCESS) return rc;
-    }
-    CUDA_OK(cudaMemcpyAsync(in->hOut, in->dOut, sizeof(double) * partitionCount, cudaMemcpyDeviceToHost, in->stream));
+    int rc = rootByPartitionLaunch(in, bufferIndices, categoryWeightsIndices, stateFrequenciesIndices,
+                                   cumulativeScaleIndices, partitionIndices, partitionCount);
+    if (rc != BEAGLE_SUCCESS) return rc;
+    const int extra = in->exchangeOn ? 2 : 0;
+    CUDA_OK(cudaMemcpyAsync(in->hOut, in->dOut, sizeof(double) * (partitionCount + extra), cudaMemcpyDeviceToHost, in->stream));
     CUDA_OK(cudaStreamSynchronize(in->stream));
     double total = 0.0;
     for (int k = 0; k < partitionCount; ++k) { outSumLogLikelihoodByPartition[k] = in->hOut[k]; total += in->hOut[k]; }
+    if (in->exchangeOn) total = in->hOut[partitionCount];      // the sum over all members of the reduce group
     *outSumLogLikelihood = total;
     return std::isnan(total) ? BEAGLE_ERROR_FLOATING_POINT : BEAGLE_SUCCESS;
 }
@@ -1979,6 +1997,19 @@ void* b200HostAlloc(long bytes) {
 }
 
 void b200HostFree(void* p) { if (p) cudaFreeHost(p); }
+
+int b200RootLogLikelihoodsByPartitionDevice(int instance, const int* bufferIndices, const int* categoryWeightsIndices,
+                                            const int* stateFrequenciesIndices, const int* cumulativeScaleIndices,
+                                            const int* partitionIndices, int partitionCount, void** outDevicePointer,
+                                            void** outStream) {
+    GET_INSTANCE(in, instance);
+    int rc = rootByPartitionLaunch(in, bufferIndices, categoryWeightsIndices, stateFrequenciesIndices,
+                                   cumulativeScaleIndices, partitionIndices, partitionCount);
+    if (rc != BEAGLE_SUCCESS) return rc;
+    if (outDevicePointer) *outDevicePointer = in->dOut;
+    if (outStream) *outStream = in->stream;
+    return BEAGLE_SUCCESS;
+}
 
 int b200RootLogLikelihoodDevice(int instance, int bufferIndex, int categoryWeightsIndex, int stateFrequenciesIndex,
                                 int cumulativeScaleIndex, void** outDevicePointer, void** outStream) {

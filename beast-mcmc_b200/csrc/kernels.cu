@@ -1779,6 +1779,35 @@ __device__ __forceinline__ unsigned long long loadSys(const unsigned long long* 
     return v;
 }
 
+// Called by one whole block (>= size threads, all of them): stores `mine` into every member's slot array, waits for the
+// others' entries of this evaluation on the own device and leaves out[0] = sum in rank order, out[1] = mine.
+__device__ __forceinline__ void exchangeJoint(const Exchange& ex, double mine, double* __restrict__ out) {
+    __shared__ double theirs[kMaxGroup];
+    const int bank = (int)(ex.seq & 1ull);
+    if ((int)threadIdx.x < ex.size) {
+        const int q = threadIdx.x;
+        ExchangeSlot* dst = ex.peers[q] + bank * ex.size + ex.rank;
+        dst->value = mine;
+        __threadfence_system();
+        storeSys(&dst->seq, ex.seq);
+        const ExchangeSlot* src = ex.peers[ex.rank] + bank * ex.size + q;         // own device's copy of member q's entry
+        const long long t0 = clock64();
+        bool ok = true;
+        while (loadSys(&src->seq) != ex.seq) {
+            if (clock64() - t0 > ex.timeoutCycles) { ok = false; break; }
+            __nanosleep(64);
+        }
+        theirs[q] = ok ? src->value : __longlong_as_double(0x7ff8000000000000ll);   // a peer never arrived: NaN
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double joint = 0.0;
+        for (int q = 0; q < ex.size; ++q) joint += theirs[q];                     // rank order: identical on every member
+        out[0] = joint;
+        out[1] = mine;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_root(const double* __restrict__ root, const double* __restrict__ weights, const double* __restrict__ freqs,
        const double* __restrict__ cumScale, const double* __restrict__ patternWeights, int S, int Sp, int C,
@@ -1828,33 +1857,27 @@ k_root(const double* __restrict__ root, const double* __restrict__ weights, cons
             return;
         }
         // ---- reduce group: this shard's sum goes to every member over NVLink, theirs are added here (engine.h, Exchange)
-        __shared__ double theirs[kMaxGroup];
-        const double mine = red[0];
-        const int bank = (int)(ex.seq & 1ull);
-        if (threadIdx.x < ex.size) {
-            const int q = threadIdx.x;
-            ExchangeSlot* dst = ex.peers[q] + bank * ex.size + ex.rank;
-            dst->value = mine;
-            __threadfence_system();
-            storeSys(&dst->seq, ex.seq);
-            const ExchangeSlot* src = ex.peers[ex.rank] + bank * ex.size + q;     // own device's copy of member q's entry
-            const long long t0 = clock64();
-            bool ok = true;
-            while (loadSys(&src->seq) != ex.seq) {
-                if (clock64() - t0 > ex.timeoutCycles) { ok = false; break; }
-                __nanosleep(64);
-            }
-            theirs[q] = ok ? src->value : __longlong_as_double(0x7ff8000000000000ll);   // a peer never arrived: NaN
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double joint = 0.0;
-            for (int q = 0; q < ex.size; ++q) joint += theirs[q];                 // rank order: identical on every member
-            out[0] = joint;
-            out[1] = mine;
-            *counter = 0u;
-        }
+        exchangeJoint(ex, red[0], out);
+        if (threadIdx.x == 0) *counter = 0u;
     }
+}
+
+// sum of `n` device values (the per-partition sums of a *ByPartition root call), then the same exchange: one block
+__global__ void __launch_bounds__(64)
+k_exchange_sum(const double* __restrict__ vals, int n, double* __restrict__ out, const Exchange ex) {
+    __shared__ double mine;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s += vals[k];
+        mine = s;
+    }
+    __syncthreads();
+    exchangeJoint(ex, mine, out);
+}
+
+cudaError_t launchExchangeSum(Instance* in, const double* dVals, int n, double* dOutJoint, const Exchange* exchange) {
+    k_exchange_sum<<<1, 64, 0, in->stream>>>(dVals, n, dOutJoint, *exchange);
+    return cudaGetLastError();
 }
 
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,

@@ -345,6 +345,14 @@ BEAGLE_DLLEXPORT int b200ExchangeConnectLocal(const int* instances, int count);
 BEAGLE_DLLEXPORT int b200ExchangeCreate(int instance, int rank, int size, void* outIpcHandle64);
 BEAGLE_DLLEXPORT int b200ExchangeConnect(int instance, const void* allIpcHandles64);
 
+/* Asynchronous variant of beagleCalculateRootLogLikelihoodsByPartition: per-partition sums stay in device memory
+ * ([0..partitionCount) at *outDevicePointer, followed by {joint, own total} for a member of a reduce group). */
+BEAGLE_DLLEXPORT int b200RootLogLikelihoodsByPartitionDevice(int instance, const int* bufferIndices,
+                                                             const int* categoryWeightsIndices,
+                                                             const int* stateFrequenciesIndices,
+                                                             const int* cumulativeScaleIndices, const int* partitionIndices,
+                                                             int partitionCount, void** outDevicePointer, void** outStream);
+
 /* The step before the path: SitePatterns.addPatterns with CompressionType.UNIQUE_ONLY
  * (src/dr/evolution/alignment/SitePatterns.java:226-372) on the GPU.  inStates is [taxon][site] (the int state codes
  * SiteList.getSitePattern yields, any values); results: outSitePatternIndices[site], outPatterns [taxon][*outPatternCount]

@@ -4,12 +4,12 @@
 W=${1:-gtr_g4_1000x10k}
 OUT=${2:-gpurun_out/r02_sweep_walk4e.txt}
 mkdir -p gpurun_out
-python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1     # alignment cache
+python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1     # alignment cache
 : > $OUT
 run() {   # label, env assignments...
   local label=$1; shift
   echo -n "$label | " >> $OUT
-  env "$@" python tools/bench_line.py --workload $W --steps ${STEPS:-200} --warmup 10 --no-cpu-baseline >> $OUT 2>&1
+  env "$@" python tools/bench_line.py --workload $W --steps ${STEPS:-200} --warmup 10 --no-cpu-baseline --no-extras >> $OUT 2>&1
 }
 run "matrix form k_walk4 (round 1)    " B200_EIGEN_WALK=0
 run "eigen R4 minb4 tip=table         " B200_EIGEN_WALK=1
