@@ -1402,6 +1402,28 @@ int beagleSetDifferentialMatrix(int instance, int matrixIndex, const double* inM
 static int combineMatrices(int instance, const int* firstIndices, const int* secondIndices, const int* resultIndices,
                            int matrixCount, bool multiply) {
     GET_INSTANCE(in, instance);
+    if (matrixCount <= 0) return BEAGLE_SUCCESS;
+    bool alias = false;
+    for (int q = 0; q < matrixCount; ++q) {
+        if (!validRange(firstIndices[q], in->nMatrices) || !validRange(secondIndices[q], in->nMatrices) ||
+            !validRange(resultIndices[q], in->nMatrices))
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        for (int r2 = 0; r2 < matrixCount; ++r2)        // a result read (again) by any pair of the batch: ordered host path
+            alias = alias || resultIndices[q] == firstIndices[r2] || resultIndices[q] == secondIndices[r2];
+    }
+    if (!alias) {
+        // on the device: one launch for the whole batch (grid = pairs x categories), indices through the staging ring
+        std::vector<int> idx(3 * (size_t)matrixCount);
+        for (int q = 0; q < matrixCount; ++q) {
+            idx[q] = firstIndices[q]; idx[matrixCount + q] = secondIndices[q]; idx[2 * (size_t)matrixCount + q] = resultIndices[q];
+            if (in->matCP > 0) in->matEigen[resultIndices[q]] = -1;       // no spectrum: the matrix-form walk serves lists using it
+        }
+        int* d = static_cast<int*>(stage(in, idx.data(), sizeof(int) * idx.size()));
+        if (d == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+        TimedScope ts(in, T_MATRICES);
+        CUDA_OK(launchCombineMatrices(in, d, d + matrixCount, d + 2 * (size_t)matrixCount, matrixCount, multiply));
+        return BEAGLE_SUCCESS;
+    }
     const size_t n = (size_t)in->C * in->S * in->S;
     std::vector<double> a(n), b(n), r(n);
     for (int q = 0; q < matrixCount; ++q) {

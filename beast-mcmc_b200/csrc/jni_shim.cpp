@@ -39,6 +39,18 @@ struct DblOut {
     operator double*() { return p; }
 };
 
+// Read-only view of the arrays on the per-step path (operation lists, matrix indices, branch lengths, scale indices):
+// Get<Type>ArrayElements COPIES on HotSpot; GetPrimitiveArrayCritical hands out the array itself (the collector is
+// merely held off for the call).  The engine copies what it needs into its pinned staging ring and enqueues -- no JNI
+// call and no wait on another Java thread happens inside the critical region, as the JNI specification demands.
+template <typename T>
+struct CritIn {
+    JNIEnv* env; jarray arr; void* p;
+    CritIn(JNIEnv* e, jarray a) : env(e), arr(a), p(a ? e->GetPrimitiveArrayCritical(a, nullptr) : nullptr) {}
+    ~CritIn() { if (p) env->ReleasePrimitiveArrayCritical(arr, p, JNI_ABORT); }
+    operator const T*() const { return static_cast<const T*>(p); }
+};
+
 }  // namespace
 
 #define NATIVE(ret, name) extern "C" JNIEXPORT ret JNICALL Java_beagle_BeagleJNIWrapper_##name
@@ -213,42 +225,42 @@ NATIVE(jint, transposeTransitionMatrices)(JNIEnv* env, jobject, jint instance, j
 }
 NATIVE(jint, updateTransitionMatrices)(JNIEnv* env, jobject, jint instance, jint eigenIndex, jintArray prob, jintArray d1,
                                        jintArray d2, jdoubleArray lengths, jint count) {
-    IntIn a(env, prob), b(env, d1), c(env, d2);
-    DblIn t(env, lengths);
+    CritIn<int> a(env, prob), b(env, d1), c(env, d2);
+    CritIn<double> t(env, lengths);
     return beagleUpdateTransitionMatrices(instance, eigenIndex, a, b, c, t, count);
 }
 NATIVE(jint, updateTransitionMatricesWithMultipleModels)(JNIEnv* env, jobject, jint instance, jintArray eigen,
                                                          jintArray rates, jintArray prob, jintArray d1, jintArray d2,
                                                          jdoubleArray lengths, jint count) {
-    IntIn e(env, eigen), r(env, rates), a(env, prob), b(env, d1), c(env, d2);
-    DblIn t(env, lengths);
+    CritIn<int> e(env, eigen), r(env, rates), a(env, prob), b(env, d1), c(env, d2);
+    CritIn<double> t(env, lengths);
     return beagleUpdateTransitionMatricesWithMultipleModels(instance, e, r, a, b, c, t, count);
 }
 NATIVE(jint, updatePrePartials)(JNIEnv* env, jobject, jint instance, jintArray ops, jint count, jint cum) {
-    IntIn a(env, ops);
+    CritIn<int> a(env, ops);
     return beagleUpdatePrePartials(instance, reinterpret_cast<const BeagleOperation*>((const int*)a), count, cum);
 }
 NATIVE(jint, updatePrePartialsByPartition)(JNIEnv* env, jobject, jint instance, jintArray ops, jint count) {
-    IntIn a(env, ops);
+    CritIn<int> a(env, ops);
     return beagleUpdatePrePartialsByPartition(instance, reinterpret_cast<const BeagleOperationByPartition*>((const int*)a), count);
 }
 NATIVE(jint, updatePartials)(JNIEnv* env, jobject, jint instance, jintArray ops, jint count, jint cum) {
-    IntIn a(env, ops);
+    CritIn<int> a(env, ops);
     return beagleUpdatePartials(instance, reinterpret_cast<const BeagleOperation*>((const int*)a), count, cum);
 }
 NATIVE(jint, updatePartialsByPartition)(JNIEnv* env, jobject, jint instance, jintArray ops, jint count) {
-    IntIn a(env, ops);
+    CritIn<int> a(env, ops);
     return beagleUpdatePartialsByPartition(instance, reinterpret_cast<const BeagleOperationByPartition*>((const int*)a), count);
 }
 NATIVE(jint, waitForPartials)(JNIEnv* env, jobject, jint instance, jintArray dest, jint count) {
     IntIn a(env, dest); return beagleWaitForPartials(instance, a, count);
 }
 NATIVE(jint, accumulateScaleFactors)(JNIEnv* env, jobject, jint instance, jintArray idx, jint count, jint cum) {
-    IntIn a(env, idx); return beagleAccumulateScaleFactors(instance, a, count, cum);
+    CritIn<int> a(env, idx); return beagleAccumulateScaleFactors(instance, a, count, cum);
 }
 NATIVE(jint, accumulateScaleFactorsByPartition)(JNIEnv* env, jobject, jint instance, jintArray idx, jint count, jint cum,
                                                 jint part) {
-    IntIn a(env, idx); return beagleAccumulateScaleFactorsByPartition(instance, a, count, cum, part);
+    CritIn<int> a(env, idx); return beagleAccumulateScaleFactorsByPartition(instance, a, count, cum, part);
 }
 NATIVE(jint, removeScaleFactors)(JNIEnv* env, jobject, jint instance, jintArray idx, jint count, jint cum) {
     IntIn a(env, idx); return beagleRemoveScaleFactors(instance, a, count, cum);

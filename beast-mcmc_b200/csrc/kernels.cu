@@ -105,6 +105,50 @@ __global__ void k_transition(const double* __restrict__ eigenBase, size_t eigenS
     }
 }
 
+// convolveTransitionMatrices / addTransitionMatrices (SubstitutionModelDelegate.java:303-470, epoch and branch-specific
+// models): result = first x second per category, resp. first + second, on the device, written in every layout the walk
+// kernels read.  grid (pairs, C); the operands must not alias the result (the host falls back otherwise).
+__device__ __forceinline__ size_t matEntry(int matCP, int Sp, int c, int i, int j) {      // P[c][i][j] in the canonical copy
+    return matCP ? ((size_t)j * matCP + c) * 4 + i : ((size_t)c * Sp + j) * Sp + i;
+}
+__global__ void __launch_bounds__(256)
+k_combine_matrices(double* __restrict__ matBase, size_t matStride, int S, int Sp, int C, int matCP,
+                   const int* __restrict__ first, const int* __restrict__ second, const int* __restrict__ result, int multiply) {
+    const int q = blockIdx.x, c = blockIdx.y;
+    const double* A = matBase + (size_t)first[q] * matStride;
+    const double* B = matBase + (size_t)second[q] * matStride;
+    double* R = matBase + (size_t)result[q] * matStride;
+    for (int idx = threadIdx.x; idx < Sp * Sp; idx += blockDim.x) {
+        const int i = idx / Sp, j = idx % Sp;
+        double v = 0.0;
+        if (i < S && j < S) {
+            if (multiply) for (int k = 0; k < S; ++k) v += A[matEntry(matCP, Sp, c, i, k)] * B[matEntry(matCP, Sp, c, k, j)];
+            else v = A[matEntry(matCP, Sp, c, i, j)] + B[matEntry(matCP, Sp, c, i, j)];
+        }
+        R[matEntry(matCP, Sp, c, i, j)] = v;
+        if (!matCP) {
+            const size_t ld = (size_t)Sp + 4;
+            double* padded = R + (size_t)C * Sp * Sp;
+            padded[((size_t)c * Sp + i) * ld + j] = v;                                  // M[c][i][.]
+            padded[(size_t)C * Sp * ld + ((size_t)c * Sp + j) * ld + i] = v;            // MT[c][j][.]
+        } else {
+            double* mm = R + 16 * matCP;                                                // tensor-variant copies (k_walk4t)
+            mm[(size_t)c * 32 + i * 4 + j] = v;
+            mm[(size_t)c * 32 + 16 + i * 4 + j] = 0.0;
+            double* mt = mm + (size_t)C * 32;
+            mt[(size_t)c * 20 + j * 4 + i] = (j < S) ? v : ((j == S && i < S) ? 1.0 : 0.0);
+            if (j == 0) mt[(size_t)c * 20 + 16 + i] = (S == 4 && i < S) ? 1.0 : 0.0;
+        }
+    }
+}
+
+cudaError_t launchCombineMatrices(Instance* in, const int* dFirst, const int* dSecond, const int* dResult, int count, bool multiply) {
+    if (count <= 0) return cudaSuccess;
+    k_combine_matrices<<<dim3(count, in->C), 256, 0, in->stream>>>(in->dMat, in->matStride, in->S, in->Sp, in->C, in->matCP,
+                                                                   dFirst, dSecond, dResult, multiply ? 1 : 0);
+    return cudaGetLastError();
+}
+
 // Tensor-core variant for real eigen systems with S > 4: one block per (branch, category) computes
 // P = Evec * (diag(exp(lambda r t)) * Ievc) as an Sp x Sp x Sp DMMA product.  Shared memory holds
 // A = Evec [i][k] and Bt[j][k] = exp(.)_k * Ievc[k][j], both with the conflict-free (Sp+4) row stride.

@@ -69,6 +69,8 @@ enum {
     JNI_IDX_GetDoubleArrayElements = 190,
     JNI_IDX_ReleaseIntArrayElements = 195,
     JNI_IDX_ReleaseDoubleArrayElements = 198,
+    JNI_IDX_GetPrimitiveArrayCritical = 222,
+    JNI_IDX_ReleasePrimitiveArrayCritical = 223,
     JNI_IDX_ExceptionCheck = 228,
     JNI_TABLE_SLOTS = 240
 };
@@ -119,6 +121,12 @@ struct JNIEnv_ {
     }
     void ReleaseDoubleArrayElements(jdoubleArray a, jdouble* e, jint mode) {
         fn<void (*)(JNIEnv*, jdoubleArray, jdouble*, jint)>(JNI_IDX_ReleaseDoubleArrayElements)(this, a, e, mode);
+    }
+    void* GetPrimitiveArrayCritical(jarray a, jboolean* isCopy) {
+        return fn<void* (*)(JNIEnv*, jarray, jboolean*)>(JNI_IDX_GetPrimitiveArrayCritical)(this, a, isCopy);
+    }
+    void ReleasePrimitiveArrayCritical(jarray a, void* e, jint mode) {
+        fn<void (*)(JNIEnv*, jarray, void*, jint)>(JNI_IDX_ReleasePrimitiveArrayCritical)(this, a, e, mode);
     }
 };
 #else

@@ -59,8 +59,10 @@ static jsize f_GetArrayLength(JNIEnv*, jarray a) {
 }
 static jobjectArray f_NewObjectArray(JNIEnv*, jsize n, jclass, jobject) { auto* o = new FakeObj; o->kind = "object[]"; o->elems.assign(n, nullptr); return J(o); }
 static void f_SetObjectArrayElement(JNIEnv*, jobjectArray a, jsize i, jobject v) { O(a)->elems[i] = O(v); }
+static int g_critical = 0;      // open GetPrimitiveArrayCritical regions
 // element access hands out a COPY and honours the release mode, like a JVM that does not pin
 static jint* f_GetIntArrayElements(JNIEnv*, jintArray a, jboolean* isCopy) {
+    if (g_critical) { fprintf(stderr, "JNI call inside a critical region\n"); abort(); }
     if (isCopy) *isCopy = JNI_TRUE;
     auto& v = O(a)->ints; jint* c = (jint*)malloc(sizeof(jint) * (v.size() + 1)); memcpy(c, v.data(), sizeof(jint) * v.size()); return c;
 }
@@ -72,6 +74,17 @@ static void f_ReleaseIntArrayElements(JNIEnv*, jintArray a, jint* e, jint mode) 
 static jdouble* f_GetDoubleArrayElements(JNIEnv*, jdoubleArray a, jboolean* isCopy) {
     if (isCopy) *isCopy = JNI_TRUE;
     auto& v = O(a)->dbls; jdouble* c = (jdouble*)malloc(sizeof(jdouble) * (v.size() + 1)); memcpy(c, v.data(), sizeof(jdouble) * v.size()); return c;
+}
+// critical access pins: the array's own storage is handed out; a counter checks that every Get is released and that no
+// other JNI call happens in between (the specification's rule)
+static void* f_GetPrimitiveArrayCritical(JNIEnv*, jarray a, jboolean* isCopy) {
+    if (isCopy) *isCopy = JNI_FALSE;
+    ++g_critical;
+    FakeObj* o = O(a);
+    return o->kind == "int[]" ? (void*)o->ints.data() : (void*)o->dbls.data();
+}
+static void f_ReleasePrimitiveArrayCritical(JNIEnv*, jarray, void*, jint) {
+    if (--g_critical < 0) { fprintf(stderr, "unbalanced ReleasePrimitiveArrayCritical\n"); abort(); }
 }
 static void f_ReleaseDoubleArrayElements(JNIEnv*, jdoubleArray a, jdouble* e, jint mode) {
     auto& v = O(a)->dbls;
@@ -107,6 +120,8 @@ int main(int argc, char** argv) {
     table.slot[JNI_IDX_GetArrayLength] = (void*)f_GetArrayLength;
     table.slot[JNI_IDX_NewObjectArray] = (void*)f_NewObjectArray;
     table.slot[JNI_IDX_SetObjectArrayElement] = (void*)f_SetObjectArrayElement;
+    table.slot[JNI_IDX_GetPrimitiveArrayCritical] = (void*)f_GetPrimitiveArrayCritical;
+    table.slot[JNI_IDX_ReleasePrimitiveArrayCritical] = (void*)f_ReleasePrimitiveArrayCritical;
     table.slot[JNI_IDX_GetIntArrayElements] = (void*)f_GetIntArrayElements;
     table.slot[JNI_IDX_ReleaseIntArrayElements] = (void*)f_ReleaseIntArrayElements;
     table.slot[JNI_IDX_GetDoubleArrayElements] = (void*)f_GetDoubleArrayElements;

@@ -455,3 +455,48 @@ def test_two_instances_on_two_resources_from_two_threads():
     for k in range(2):
         assert len(results[k]) == 20 and all(v == serial[k] for v in results[k])
     assert _rel(results[0][0] + results[1][0], lw) <= REL
+
+
+# ---- epoch-model matrices (convolved on the device) inside an operation list ------------------------------------------------
+@pytest.mark.parametrize("states,cats", [(4, 4), (20, 2)])
+def test_convolved_matrices_in_an_operation_list(states, cats):
+    """SubstitutionModelDelegate.java:303-470: P(t1) x P(t2) per branch through convolveTransitionMatrices, then the usual
+    list.  For S = 4 such matrices carry no spectrum, so the list runs on the matrix-form walk; the value equals the oracle's
+    and (Chapman-Kolmogorov) the plain evaluation with t1 + t2."""
+    tree, pats, model, site = H.synthetic_case(24, 257, cats, seed=61, stateCount=states)
+    N, n, P, S, C = tree.tipCount, tree.nodeCount, pats.patternCount, states, cats
+    branches, nodeOps = [], []
+    like = tdl.TreeDataLikelihood.__new__(tdl.TreeDataLikelihood)
+    like.tree, like.traversalType, like.updateNode = tree, "REVERSE_LEVEL_ORDER", np.ones(n, dtype=bool)
+    like._dispatch()
+    nodes = [b for b, _ in like.branchOperations]
+    lens = np.array([t for _, t in like.branchOperations])
+    ops = []
+    for node, c1, c2 in like.nodeOperations:
+        ops += [node, NONE, NONE, c1, 2 * n + c1, c2, 2 * n + c2]          # the convolved matrices live at 2n + branch
+    vals = []
+    for factory, rl in ((GPU, [1, 0]), (H.oracle_factory(), None)):
+        b = factory(N, n, N, S, P, 1, 3 * n, C, 0, rl, 0, 0)
+        for t in range(N):
+            b.setTipStates(t, np.ascontiguousarray(pats.states[t], dtype=np.int32))
+        b.setPatternWeights(pats.weights)
+        e = model.getEigenDecomposition()
+        b.setEigenDecomposition(0, e.Evec, e.Ievc, e.Eval)
+        b.setCategoryRates(site.getCategoryRates())
+        b.setCategoryWeights(0, site.getCategoryProportions())
+        b.setStateFrequencies(0, model.getFrequencies())
+        b.updateTransitionMatrices(0, _i(nodes), None, None, 0.3 * lens, len(nodes))
+        b.updateTransitionMatrices(0, _i([n + k for k in nodes]), None, None, 0.7 * lens, len(nodes))
+        b.convolveTransitionMatrices(_i(nodes), _i([n + k for k in nodes]), _i([2 * n + k for k in nodes]), len(nodes))
+        out = np.zeros(1)
+        b.updatePartials(_i(ops), len(ops) // 7, NONE)
+        b.calculateRootLogLikelihoods(_i([tree.root]), _i([0]), _i([0]), _i([NONE]), 1, out)
+        vals.append(out[0])
+        # the same tree with the whole branch in one matrix
+        b.updateTransitionMatrices(0, _i([2 * n + k for k in nodes]), None, None, lens, len(nodes))
+        b.updatePartials(_i(ops), len(ops) // 7, NONE)
+        b.calculateRootLogLikelihoods(_i([tree.root]), _i([0]), _i([0]), _i([NONE]), 1, out)
+        vals.append(out[0])
+        b.finalize()
+    assert math.isfinite(vals[2]) and _rel(vals[0], vals[2]) <= REL, vals
+    assert _rel(vals[1], vals[3]) <= REL and _rel(vals[0], vals[1]) <= 1e-9, vals
