@@ -220,6 +220,193 @@ k_walk4e(const WalkArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_walk4p -- the same arithmetic with PER-WARP ASYNCHRONOUS OPERAND STAGING (the default for aligned lists, CP <= 8).
+//
+// What bounded k_walk4e after the matrices were gone (profiles/r02_walk4e_summary.md): every pipe below 50 %, but 38 % of the
+// stall samples "long scoreboard" on first uses of small per-op operands -- the op record, the tips' state bytes, the
+// spectra, the P columns of tip children -- i.e. a chain of dependent L1/L2 latencies per op with 16 warps per SM to hide it.
+// Those operands are tiny, warp-uniform and known one op ahead, so each warp runs a two-deep cp.async (LDGSTS) pipeline into
+// its own slice of shared memory: while op k computes, record k+2 and ALL small operands of op k+1 travel global -> shared
+// without touching a register; op k+1 finds them with shared-memory latency.  Per op and warp: three LDGSTS instructions.
+//   ring[4]            op records (64 B), fetched two ops ahead
+//   stage[k & 1]       mat[child][5][CP][4]  P block of a tip child exactly as it lies in HBM ([j][CP][i] = one contiguous
+//                                            copy), row 4 = the gap column (written once); a pattern picks its 32-B column
+//                      ev[child][CP][4]      spectrum of an internal child
+//                      st[child][G*R]        state bytes of a tip child for this warp's patterns
+// Child partials that are not forwarded in registers keep the look-ahead L1 prefetch.  Aligned lists only (every op spans
+// [0, Ppad), a warp's G*R patterns start at a multiple of 16): windows and thin R = 1 phases use k_walk4e.
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
+    const unsigned sAddr = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sAddr), "l"(gmemSrc) : "memory");
+}
+
+template <int CP, int R>
+struct WarpStage {
+    static constexpr int G = 32 / CP, NP = G * R;
+    double mat[2][5 * CP * 4];
+    double ev[2][CP * 4];
+    unsigned char st[2][NP];
+};
+
+template <int CP, int R, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_walk4p(const WalkArgs A) {
+    constexpr int G = 32 / CP, NP = G * R;
+    static_assert(NP % 16 == 0, "state bytes are staged in 16-byte pieces");
+    __shared__ __align__(16) WarpStage<CP, R> stages[4][2];
+    __shared__ __align__(16) Op4 rings[4][4];
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));            // volatile: never rematerialised as an S2R inside the loop
+    const int wib = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int c = lane / G;
+    const int4 range = __ldg(A.subs + blockIdx.y);
+    const int pBase = range.z + warp * NP;                         // first pattern of this warp
+    if (pBase >= range.w) return;
+    const int p0 = pBase + (lane % G);                             // patterns p0 + r*G
+    const bool catValid = c < A.C;
+    const int cc = catValid ? c : 0;
+    const size_t off0 = ((size_t)cc * A.Ppad + p0) * 4;
+    const int last = range.y - 1, S = A.S;
+    WarpStage<CP, R>* stage = stages[wib];
+    Op4* ring = rings[wib];
+
+    // the gap column (row 4 of every table), once
+    for (int q = lane; q < 4 * CP * 4; q += 32) {
+        const int tbl = q / (CP * 4), e = q % (CP * 4);
+        stage[tbl >> 1].mat[tbl & 1][4 * CP * 4 + e] = ((e & 3) < S) ? 1.0 : 0.0;
+    }
+    // what op j reads beyond partials goes to stage j & 1; reads record j from the ring (it has arrived)
+    auto issueOperands = [&](int j) {
+        const int4 rec = *reinterpret_cast<const int4*>(&ring[j & 3]);          // dest, c1, c2, m1
+        const int m2 = ring[j & 3].m2;
+        WarpStage<CP, R>& sg = stage[j & 1];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int child = ch == 0 ? rec.y : rec.z, m = ch == 0 ? rec.w : m2;
+            if (child < 0) {
+                const double* src = A.mats + (size_t)m * A.matStride;          // [j][CP][i]: 4 * CP * 4 doubles, contiguous
+#pragma unroll
+                for (int q = lane; q < CP * 8; q += 32) cpAsync16(&sg.mat[ch][2 * q], src + 2 * q);
+            } else if (lane < CP * 2) {
+                cpAsync16(&sg.ev[ch][2 * lane], A.evecs + (size_t)m * CP * 4 + 2 * lane);
+            }
+        }
+        // one more instruction: state bytes of the tip children (lanes 4 ..) and, on lanes 0-3, record j + 1
+        constexpr int SL = NP / 16;
+        if (lane < 4) {
+            if (j + 1 <= last) cpAsync16(reinterpret_cast<char*>(&ring[(j + 1) & 3]) + 16 * lane,
+                                         reinterpret_cast<const char*>(A.ops + j + 1) + 16 * lane);
+        } else if (lane < 4 + 2 * SL) {
+            const int ch = (lane - 4) / SL, piece = (lane - 4) % SL;
+            const int child = ch == 0 ? rec.y : rec.z;
+            if (child < 0)
+                cpAsync16(&sg.st[ch][16 * piece], A.states + (size_t)(-child - 1) * A.Ppad + pBase + 16 * piece);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // prologue: records k0 (and k0+1 through issueOperands), then the operands of k0
+    if (lane < 4) cpAsync16(reinterpret_cast<char*>(&ring[range.x & 3]) + 16 * lane,
+                            reinterpret_cast<const char*>(A.ops + range.x) + 16 * lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    issueOperands(range.x);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+
+    double Vi[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) asm volatile("mov.f64 %0, %1;" : "=d"(Vi[q]) : "d"(A.Vi[q]));
+    double d[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.0;
+
+    for (int k = range.x; k <= last; ++k) {
+        if (k + 1 <= last) issueOperands(k + 1);                   // travels while op k computes
+        const Op4 cur = ring[k & 3];
+        const WarpStage<CP, R>& sg = stage[k & 1];
+        // look-ahead for the child partials of op k+1 that are not forwarded (never this op's destination)
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int pf = w == 0 ? cur.pfA : cur.pfB;
+            if (pf == 0 || (pf & 1) || !catValid) continue;
+            const double* xg = A.partials + (size_t)((pf >> 1) - 1) * A.stride + off0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) prefetchL1(xg + (size_t)r * G * 4);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int child = ch == 0 ? cur.c1 : cur.c2;
+            if (child < 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int sym = sg.st[ch][(lane % G) + r * G];
+                    const double2* col = reinterpret_cast<const double2*>(&sg.mat[ch][((sym < S ? sym : 4) * CP + cc) * 4]);
+                    const double2 lo = col[0], hi = col[1];
+                    if (ch == 0) { d[r][0] = lo.x; d[r][1] = lo.y; d[r][2] = hi.x; d[r][3] = hi.y; }
+                    else { d[r][0] *= lo.x; d[r][1] *= lo.y; d[r][2] *= hi.x; d[r][3] *= hi.y; }
+                }
+            } else {
+                const double2* ep = reinterpret_cast<const double2*>(&sg.ev[ch][cc * 4]);
+                const double2 e01 = ep[0], e23 = ep[1];
+                const double e[4] = {e01.x, e01.y, e23.x, e23.y};
+                const bool fromRegisters = ch == 0 && (cur.pad_ & 2) != 0;
+                const double* xg = A.partials + (size_t)child * A.stride + off0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double x[4], u[4], y[4];
+                    if (fromRegisters) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x[i] = d[r][i];
+                    } else {
+                        ldg256(xg + (size_t)r * G * 4, x);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        u[q] = (Vi[4 * q] * x[0] + Vi[4 * q + 1] * x[1] + Vi[4 * q + 2] * x[2] + Vi[4 * q + 3] * x[3]) * e[q];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        y[i] = absBits(A.V[4 * i] * u[0] + A.V[4 * i + 1] * u[1] + A.V[4 * i + 2] * u[2] + A.V[4 * i + 3] * u[3]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[r][i] = ch == 0 ? y[i] : d[r][i] * y[i];
+                }
+            }
+        }
+        double* dg = A.partials + (size_t)cur.dest * A.stride + off0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r * G;
+            if (cur.sw >= 0) {                 // rescaling (AbstractLikelihoodCore.java:406-442, unconditional as in BEAGLE)
+                double m = catValid ? fmax(fmax(d[r][0], d[r][1]), fmax(d[r][2], d[r][3])) : 0.0;
+#pragma unroll
+                for (int sh = G; sh < 32; sh <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, sh));
+                if (m == 0.0) m = 1.0;
+                const double inv = 1.0 / m;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[r][i] *= inv;
+                if (c == 0) A.scale[(size_t)cur.sw * A.Ppad + p] = A.logScalers ? log(m) : m;
+            } else if (cur.sr >= 0) {
+                double f = A.scale[(size_t)cur.sr * A.Ppad + p];
+                if (A.logScalers) f = exp(f);
+                const double inv = 1.0 / f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[r][i] *= inv;
+            }
+            if (catValid) stg256(dg + (size_t)r * G * 4, d[r]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // op k+1's operands and record k+2 have landed
+        __syncwarp();
+    }
+}
+
+template <int CP, int R, int MINB>
+cudaError_t launchP(Instance* in, const WalkArgs& A, dim3 grid) {
+    k_walk4p<CP, R, MINB><<<grid, 128, 0, in->stream>>>(A);
+    return cudaGetLastError();
+}
+
 template <int CP, int R, bool ALIGNED, int MINB, int TIP>
 cudaError_t launchK(Instance* in, const WalkArgs& A, dim3 grid) {
     k_walk4e<CP, R, ALIGNED, MINB, TIP><<<grid, 128, 0, in->stream>>>(A);
@@ -237,6 +424,17 @@ cudaError_t launchR(Instance* in, WalkArgs& A, int nSubs, int maxWindow, bool al
     dim3 grid((warps + 3) / 4, nSubs);
     // predicate-free only when a warp's G*R patterns can never straddle the end of the padded pattern axis
     if (!aligned || in->Ppad % (G * R) != 0) return launchK<CP, R, false, 4, TIPD>(in, A, grid);
+    if constexpr (CP <= 8 && (G * R) % 16 == 0) {
+        if (in->tipMode == 3) {                 // per-warp asynchronous operand staging (k_walk4p)
+            if constexpr (CP == 4) {
+                const int minb = in->walkMinBlocks;
+                if (minb >= 6) return launchP<CP, R, 6>(in, A, grid);
+                if (minb == 5) return launchP<CP, R, 5>(in, A, grid);
+                if (minb == 3) return launchP<CP, R, 3>(in, A, grid);
+            }
+            return launchP<CP, R, 4>(in, A, grid);
+        }
+    }
     if constexpr (CP == 4 && R >= 2) {
         const int minb = in->walkMinBlocks, tip = in->tipMode;
         if (tip == 0) {

@@ -15,10 +15,34 @@
  * independent.  Pinned by tests/test_oracle_golden.py::test_c_port_* against the reference's ten
  * golden log-likelihoods and against the numpy oracle.
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
+#include <stdatomic.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
+
+/* Sense-reversing spin barrier (pause, then yield): a likelihood evaluation is a handful of jobs a few milliseconds long,
+ * and a futex-based pthread_barrier with ~100 waiters costs as much as a job on a busy host. */
+typedef struct { atomic_int count; atomic_int sense; int n; } SpinBarrier;
+static void sb_init(SpinBarrier* b, int n) { atomic_init(&b->count, 0); atomic_init(&b->sense, 0); b->n = n; }
+static void sb_wait(SpinBarrier* b, int* localSense) {
+    *localSense = !*localSense;
+    if (atomic_fetch_add_explicit(&b->count, 1, memory_order_acq_rel) == b->n - 1) {
+        atomic_store_explicit(&b->count, 0, memory_order_relaxed);
+        atomic_store_explicit(&b->sense, *localSense, memory_order_release);
+    } else {
+        int spins = 0;
+        while (atomic_load_explicit(&b->sense, memory_order_acquire) != *localSense) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            if (++spins > 20000) { sched_yield(); spins = 0; }
+        }
+    }
+}
 
 typedef struct {
     int tipCount, nBuffers, S, P, nEigen, nMatrices, C, nScale, threads, logScalers;
@@ -34,7 +58,8 @@ typedef struct {
     double* site;
     /* persistent worker pool (threads-1 workers + the caller), two barriers per job */
     pthread_t* workers;
-    pthread_barrier_t startBar, endBar;
+    SpinBarrier startBar, endBar;
+    int callerSense[2];
     int poolReady, quit, jobKind;
     /* job arguments */
     const int* jobOps; int jobNOps, jobCum;
@@ -49,11 +74,21 @@ static void* worker_main(void* arg) {
     OracleCpu* o = w->o;
     const int tid = w->tid;
     free(w);
+    /* one worker per hardware thread, pinned: the pattern block a thread owns stays on the NUMA node that first touched
+     * it (the partials are first written inside the walk, by the owning thread) */
+    const long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    if (ncpu > 0 && o->threads <= ncpu) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET((int)(tid % ncpu), &set);
+        pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+    }
+    int s0 = 0, s1 = 0;
     for (;;) {
-        pthread_barrier_wait(&o->startBar);
+        sb_wait(&o->startBar, &s0);
         if (o->quit) break;
         run_job(o, tid);
-        pthread_barrier_wait(&o->endBar);
+        sb_wait(&o->endBar, &s1);
     }
     return NULL;
 }
@@ -61,8 +96,9 @@ static void* worker_main(void* arg) {
 static void pool_run(OracleCpu* o, int kind) {
     if (o->threads <= 1) { o->jobKind = kind; run_job(o, 0); return; }
     if (!o->poolReady) {
-        pthread_barrier_init(&o->startBar, NULL, o->threads);
-        pthread_barrier_init(&o->endBar, NULL, o->threads);
+        sb_init(&o->startBar, o->threads);
+        sb_init(&o->endBar, o->threads);
+        o->callerSense[0] = o->callerSense[1] = 0;
         o->workers = (pthread_t*)malloc(sizeof(pthread_t) * o->threads);
         for (int t = 1; t < o->threads; ++t) {
             WorkerArg* w = (WorkerArg*)malloc(sizeof(WorkerArg));
@@ -72,9 +108,9 @@ static void pool_run(OracleCpu* o, int kind) {
         o->poolReady = 1;
     }
     o->jobKind = kind;
-    pthread_barrier_wait(&o->startBar);
+    sb_wait(&o->startBar, &o->callerSense[0]);
     run_job(o, 0);
-    pthread_barrier_wait(&o->endBar);
+    sb_wait(&o->endBar, &o->callerSense[1]);
 }
 
 #define EXPORT __attribute__((visibility("default")))
@@ -103,9 +139,8 @@ EXPORT OracleCpu* oc_create(int tipCount, int nBuffers, int S, int P, int nEigen
 EXPORT void oc_free(OracleCpu* o) {
     if (o->poolReady) {
         o->quit = 1;
-        pthread_barrier_wait(&o->startBar);
+        sb_wait(&o->startBar, &o->callerSense[0]);
         for (int t = 1; t < o->threads; ++t) pthread_join(o->workers[t], NULL);
-        pthread_barrier_destroy(&o->startBar); pthread_barrier_destroy(&o->endBar);
         free(o->workers);
     }
     for (int b = 0; b < o->nBuffers; ++b) { free(o->partials[b]); free(o->states[b]); }
@@ -189,6 +224,55 @@ static void child_term(const OracleCpu* o, int buf, int mat, int c, int p, doubl
     }
 }
 
+/* dest[c][p][:] = (M1_c x1[c][p][:]) * (M2_c x2[c][p][:]) for the patterns [p0, p1): the same arithmetic as the scalar
+ * statement of GeneralLikelihoodCore.java:171-203 with the four parent states of a cell held in one vector
+ * (u = M[:,0] x0 + M[:,1] x1 + M[:,2] x2 + M[:,3] x3).  target_clones: the binary is built once and travels to another
+ * host, so the instruction set is picked at load time. */
+typedef double v4d __attribute__((vector_size(32), aligned(8)));
+__attribute__((target_clones("avx2,fma", "default")))
+static void walk4_op(const OracleCpu* o, const int* op, double* dest, int p0, int p1) {
+    const int C = o->C, P = o->P;
+    for (int c = 0; c < C; ++c) {
+        const double* M1 = o->matrices + ((size_t)op[4] * C + c) * 16;
+        const double* M2 = o->matrices + ((size_t)op[6] * C + c) * 16;
+        v4d a[5], b[5];                                  /* columns of the two matrices; column 4 = gap (all ones) */
+        for (int j = 0; j < 4; ++j) {
+            a[j] = (v4d){M1[j], M1[4 + j], M1[8 + j], M1[12 + j]};
+            b[j] = (v4d){M2[j], M2[4 + j], M2[8 + j], M2[12 + j]};
+        }
+        a[4] = b[4] = (v4d){1.0, 1.0, 1.0, 1.0};
+        const int* s1 = o->states[op[3]];
+        const int* s2 = o->states[op[5]];
+        const double* x1 = s1 ? NULL : o->partials[op[3]] + (size_t)c * P * 4;
+        const double* x2 = s2 ? NULL : o->partials[op[5]] + (size_t)c * P * 4;
+        double* d = dest + (size_t)c * P * 4;
+        if (!s1 && !s2) {
+            for (int p = p0; p < p1; ++p) {
+                const double* x = x1 + 4 * p;
+                const double* y = x2 + 4 * p;
+                const v4d u = a[0] * x[0] + a[1] * x[1] + a[2] * x[2] + a[3] * x[3];
+                const v4d v = b[0] * y[0] + b[1] * y[1] + b[2] * y[2] + b[3] * y[3];
+                *(v4d*)(d + 4 * p) = u * v;
+            }
+        } else if (s1 && s2) {
+            for (int p = p0; p < p1; ++p) {
+                const int sa = s1[p] < 4 ? s1[p] : 4, sb = s2[p] < 4 ? s2[p] : 4;
+                *(v4d*)(d + 4 * p) = a[sa] * b[sb];
+            }
+        } else {
+            const int* st = s1 ? s1 : s2;
+            const v4d* tc = s1 ? a : b;                  /* tip child's columns */
+            const v4d* ic = s1 ? b : a;                  /* internal child's matrix */
+            const double* xi = s1 ? x2 : x1;
+            for (int p = p0; p < p1; ++p) {
+                const double* x = xi + 4 * p;
+                const v4d u = ic[0] * x[0] + ic[1] * x[1] + ic[2] * x[2] + ic[3] * x[3];
+                *(v4d*)(d + 4 * p) = u * tc[st[p] < 4 ? st[p] : 4];
+            }
+        }
+    }
+}
+
 static void* walk_block(void* arg) {
     WalkJob* w = (WalkJob*)arg;
     OracleCpu* o = w->o;
@@ -197,24 +281,8 @@ static void* walk_block(void* arg) {
     for (int k = 0; k < w->nOps; ++k) {
         const int* op = w->ops + 7 * k;
         double* dest = o->partials[op[0]];
-        if (S == 4) {          /* nucleotide fast path: same arithmetic, unrolled */
-            for (int c = 0; c < C; ++c) {
-                const double* M1 = o->matrices + ((size_t)op[4] * C + c) * 16;
-                const double* M2 = o->matrices + ((size_t)op[6] * C + c) * 16;
-                const int* s1 = o->states[op[3]];
-                const int* s2 = o->states[op[5]];
-                const double* x1 = s1 ? NULL : o->partials[op[3]] + (size_t)c * P * 4;
-                const double* x2 = s2 ? NULL : o->partials[op[5]] + (size_t)c * P * 4;
-                double* d = dest + (size_t)c * P * 4;
-                for (int p = w->p0; p < w->p1; ++p) {
-                    double u[4], v[4];
-                    if (s1) { int s = s1[p]; for (int i = 0; i < 4; ++i) u[i] = s < 4 ? M1[i * 4 + s] : 1.0; }
-                    else { const double* x = x1 + 4 * p; for (int i = 0; i < 4; ++i) u[i] = M1[i*4]*x[0] + M1[i*4+1]*x[1] + M1[i*4+2]*x[2] + M1[i*4+3]*x[3]; }
-                    if (s2) { int s = s2[p]; for (int i = 0; i < 4; ++i) v[i] = s < 4 ? M2[i * 4 + s] : 1.0; }
-                    else { const double* x = x2 + 4 * p; for (int i = 0; i < 4; ++i) v[i] = M2[i*4]*x[0] + M2[i*4+1]*x[1] + M2[i*4+2]*x[2] + M2[i*4+3]*x[3]; }
-                    for (int i = 0; i < 4; ++i) d[4 * p + i] = u[i] * v[i];
-                }
-            }
+        if (S == 4) {          /* nucleotide fast path: one 4-state cell = one 256-bit vector (AVX2 + FMA clone) */
+            walk4_op(o, op, dest, w->p0, w->p1);
         } else {
             for (int c = 0; c < C; ++c)
                 for (int p = w->p0; p < w->p1; ++p) {

@@ -12,16 +12,14 @@ run() {   # label, env assignments...
   env "$@" python tools/bench_line.py --workload $W --steps ${STEPS:-200} --warmup 10 --no-cpu-baseline --no-extras >> $OUT 2>&1
 }
 run "matrix form k_walk4 (round 1)    " B200_EIGEN_WALK=0
-run "eigen R4 minb4 tip=table         " B200_EIGEN_WALK=1
-run "eigen R4 minb5 tip=table         " B200_WALK_MINB=5
-run "eigen R4 minb6 tip=table         " B200_WALK_MINB=6
-run "eigen R4 minb3 tip=table         " B200_WALK_MINB=3
-run "eigen R2 minb4 tip=table         " B200_WALK_R=2
-run "eigen R2 minb5 tip=table         " B200_WALK_R=2 B200_WALK_MINB=5
-run "eigen R2 minb6 tip=table         " B200_WALK_R=2 B200_WALK_MINB=6
-run "eigen R8 minb4 tip=table (pred.) " B200_WALK_R=8
-run "eigen R4 minb4 tip=contraction   " B200_TIP_MODE=0
-run "eigen R4 minb4 tip=P column      " B200_TIP_MODE=1
-run "eigen R4 minb4 table oversub 2   " B200_PHASE_OVERSUB=2
-run "eigen R4 minb4 table no lookahead" B200_LOOKAHEAD=0
+run "eigen async-staged R4 minb4      " B200_TIP_MODE=3
+run "eigen async-staged R4 minb5      " B200_TIP_MODE=3 B200_WALK_MINB=5
+run "eigen async-staged R4 minb6      " B200_TIP_MODE=3 B200_WALK_MINB=6
+run "eigen async-staged R4 minb3      " B200_TIP_MODE=3 B200_WALK_MINB=3
+run "eigen async-staged R2 minb4      " B200_TIP_MODE=3 B200_WALK_R=2
+run "eigen async-staged R2 minb6      " B200_TIP_MODE=3 B200_WALK_R=2 B200_WALK_MINB=6
+run "eigen async-staged R4 minb5 ovs2 " B200_TIP_MODE=3 B200_WALK_MINB=5 B200_PHASE_OVERSUB=2
+run "eigen async-staged R4 minb5 nola " B200_TIP_MODE=3 B200_WALK_MINB=5 B200_LOOKAHEAD=0
+run "eigen table        R4 minb5      " B200_TIP_MODE=2 B200_WALK_MINB=5
+run "eigen contraction  R4 minb4      " B200_TIP_MODE=0
 cat $OUT
