@@ -166,6 +166,7 @@ _SIGNATURES = {
     "b200GetKernelTiming": ([_I, _I, _DP, C.POINTER(C.c_long)], _I),
     "b200CompressSitePatterns": ([_I, _I, _I, _IP, _DP, _IP, _IP, _DP, _IP], _I),
     "b200GetSourceHash": ([], C.c_char_p),
+    "b200GetFusedLaunches": ([_I], _L),
     "b200RootLogLikelihoodsByPartitionDevice": ([_I, _IP, _IP, _IP, _IP, _IP, _I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)], _I),
     "b200SetShardDevices": ([_IP, _I], _I),
     "b200ExchangeConnectLocal": ([_IP, _I], _I),

@@ -11,6 +11,7 @@
 #include "multi.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -38,6 +39,8 @@ int envInt(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+int flushPending(Instance* in);
+
 Instance* getInstance(int id) {
     std::lock_guard<std::mutex> lock(gMutex);
     if (id < 0 || id >= (int)gInstances.size()) return nullptr;
@@ -55,11 +58,20 @@ Instance* getInstance(int id) {
         }                                                                                    \
     } while (0)
 
-#define GET_INSTANCE(in, id)                                            \
+// GET_INSTANCE_LAZY: the three calls of a deferred small evaluation (incr.cu) manage the pending work themselves;
+// GET_INSTANCE: every other entry point first launches whatever was deferred, so that it observes completed semantics
+#define GET_INSTANCE_LAZY(in, id)                                       \
     Instance* in = getInstance(id);                                     \
     if (in == nullptr) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;      \
     if (in->shard != nullptr) return BEAGLE_ERROR_NO_IMPLEMENTATION;    \
     if (cudaSetDevice(in->device) != cudaSuccess) return BEAGLE_ERROR_GENERAL;
+
+#define GET_INSTANCE(in, id)                                            \
+    GET_INSTANCE_LAZY(in, id)                                           \
+    if (!in->pendingMats.empty() || !in->pendingOps.empty()) {          \
+        const int flushRc__ = flushPending(in);                         \
+        if (flushRc__ != BEAGLE_SUCCESS) return flushRc__;              \
+    }
 
 #define CUDA_OK(expr)                                                                        \
     do {                                                                                     \
@@ -146,7 +158,8 @@ void destroyInstance(Instance* in) {
     if (in->stream) cudaStreamSynchronize(in->stream);
     cudaFree(in->partialsBase); cudaFree(in->states8Base); cudaFree(in->states32Base);
     for (CachedPlan& cp : in->planCache) { if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec); cudaFree(cp.dBlock); }
-    cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dEvec); cudaFree(in->dRates); cudaFree(in->dWeights);
+    cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dEvec); cudaFree(in->dIncSums); cudaFree(in->dIncCounter);
+    if (in->hMapped) cudaFreeHost(in->hMapped); cudaFree(in->dRates); cudaFree(in->dWeights);
     cudaFree(in->dFreqs); cudaFree(in->dScale); cudaFree(in->dPatternWeights);
     cudaFree(in->dPatternPartitions); cudaFree(in->dSite); cudaFree(in->dBlockSums); cudaFree(in->dOut);
     cudaFree(in->dCounter); cudaFree(in->dStage); cudaFree(in->dScratch);
@@ -457,6 +470,38 @@ void noteScaleWrites(Instance* in, const std::vector<HostOp>& hops) {
     for (const HostOp& o : hops) if (o.sw >= 0) in->scaleIsLog[o.sw] = in->logScalers ? 1 : 0;
 }
 
+// validation (no side effects) of an operation list, then lazy allocation / kind changes of its destinations
+int prepareOps(Instance* in, const std::vector<HostOp>& hops, bool byPartition) {
+    for (const HostOp& o : hops) {
+        if (!validRange(o.dest, in->nBuffers) || !validRange(o.c1, in->nBuffers) ||
+            !validRange(o.c2, in->nBuffers) || !validRange(o.m1, in->nMatrices) ||
+            !validRange(o.m2, in->nMatrices))
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (o.sw != BEAGLE_OP_NONE && !validRange(o.sw, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (o.sr != BEAGLE_OP_NONE && !validRange(o.sr, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (o.cum != BEAGLE_OP_NONE && !validRange(o.cum, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (byPartition && !validRange(o.part, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    }
+    {
+        // a child must hold data: compact states, partials, or the destination of an op of this very list
+        std::vector<char> written(in->nBuffers, 0);
+        for (const HostOp& o : hops) written[o.dest] = 1;
+        auto holdsData = [&](int b) { return written[b] || in->partials[b] != nullptr || in->states32[b] != nullptr; };
+        for (const HostOp& o : hops) {
+            if (!holdsData(o.c1) || !holdsData(o.c2)) return BEAGLE_ERROR_OUT_OF_RANGE;
+            // pre-order: c1 is pre[parent], a partials buffer by construction
+            if (o.kind == 1 && !written[o.c1] && in->states32[o.c1] != nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
+        }
+    }
+    for (const HostOp& o : hops) {
+        if (ensurePartials(in, o.dest) == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
+        if (in->states32[o.dest] != nullptr) in->bufferEpoch++;
+        in->states8[o.dest] = nullptr;      // a written buffer holds partials from now on
+        in->states32[o.dest] = nullptr;
+    }
+    return BEAGLE_SUCCESS;
+}
+
 // The eigen-form walk serves a post-order 4-state list when every matrix it names was computed by
 // updateTransitionMatrices from the CURRENT content of ONE real eigen slot; returns that slot or -1.
 int eigenFormSlot(const Instance* in, const std::vector<HostOp>& hops) {
@@ -528,33 +573,9 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             return BEAGLE_SUCCESS;
         }
     }
-    // ---- validation (no side effects), then lazy allocation / kind changes
-    for (const HostOp& o : hops) {
-        if (!validRange(o.dest, in->nBuffers) || !validRange(o.c1, in->nBuffers) ||
-            !validRange(o.c2, in->nBuffers) || !validRange(o.m1, in->nMatrices) ||
-            !validRange(o.m2, in->nMatrices))
-            return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (o.sw != BEAGLE_OP_NONE && !validRange(o.sw, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (o.sr != BEAGLE_OP_NONE && !validRange(o.sr, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (o.cum != BEAGLE_OP_NONE && !validRange(o.cum, in->nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (byPartition && !validRange(o.part, in->partitionCount)) return BEAGLE_ERROR_OUT_OF_RANGE;
-    }
     {
-        // a child must hold data: compact states, partials, or the destination of an op of this very list
-        std::vector<char> written(in->nBuffers, 0);
-        for (const HostOp& o : hops) written[o.dest] = 1;
-        auto holdsData = [&](int b) { return written[b] || in->partials[b] != nullptr || in->states32[b] != nullptr; };
-        for (const HostOp& o : hops) {
-            if (!holdsData(o.c1) || !holdsData(o.c2)) return BEAGLE_ERROR_OUT_OF_RANGE;
-            // pre-order: c1 is pre[parent], a partials buffer by construction
-            if (o.kind == 1 && !written[o.c1] && in->states32[o.c1] != nullptr) return BEAGLE_ERROR_OUT_OF_RANGE;
-        }
-    }
-    for (const HostOp& o : hops) {
-        if (ensurePartials(in, o.dest) == nullptr) return BEAGLE_ERROR_OUT_OF_MEMORY;
-        if (in->states32[o.dest] != nullptr) in->bufferEpoch++;
-        in->states8[o.dest] = nullptr;      // a written buffer holds partials from now on
-        in->states32[o.dest] = nullptr;
+        const int rcPrepare = prepareOps(in, hops, byPartition);
+        if (rcPrepare != BEAGLE_SUCCESS) return rcPrepare;
     }
     const bool fourState = in->matCP > 0;
     Plan plan;
@@ -1011,6 +1032,22 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     alloc(&in->dEigen, std::max(1, in->nEigen) * eigenStride);
     alloc(&in->dMat, matElems);
     if (in->matCP > 0) alloc(&in->dEvec, (size_t)in->nMatrices * in->matCP * 4);
+    if (in->matCP > 0 && in->matCP <= 8) {
+        alloc(&in->dIncSums, (size_t)in->Ppad / 4 + 8);
+        alloc(&in->dIncCounter, 4);
+        in->fuseSmall = envInt("B200_FUSE", 1);
+        if (ok && in->fuseSmall) {
+            // the fused evaluation lands its result here; without mapped memory the fusion is simply off
+            if (cudaHostAlloc(reinterpret_cast<void**>(&in->hMapped), 64, cudaHostAllocMapped) == cudaSuccess &&
+                cudaHostGetDevicePointer(reinterpret_cast<void**>(&in->dMapped), in->hMapped, 0) == cudaSuccess) {
+                memset(in->hMapped, 0, 64);
+            } else {
+                cudaGetLastError();
+                if (in->hMapped) cudaFreeHost(in->hMapped);
+                in->hMapped = nullptr;
+            }
+        }
+    }
     alloc(&in->dRates, (size_t)in->nSets * in->C);
     alloc(&in->dWeights, (size_t)in->nSets * in->C);
     alloc(&in->dFreqs, (size_t)in->nSets * in->Sp);
@@ -1319,13 +1356,128 @@ static int updateMatricesImpl(Instance* in, const int* eigenIndices, int eigenIn
     return BEAGLE_SUCCESS;
 }
 
+// ---- deferred small evaluations (incr.cu) --------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+int flushPendingImpl(Instance* in) {
+    int rc = BEAGLE_SUCCESS;
+    if (!in->pendingMats.empty()) {
+        const int n = (int)in->pendingMats.size();
+        std::vector<int> eig(n), rate(n), prob(n);
+        std::vector<double> len(n);
+        for (int k = 0; k < n; ++k) {
+            eig[k] = in->pendingMats[k].eigen; rate[k] = in->pendingMats[k].rateSet;
+            prob[k] = in->pendingMats[k].prob; len[k] = in->pendingMats[k].len;
+        }
+        in->pendingMats.clear();
+        rc = updateMatricesImpl(in, eig.data(), 0, rate.data(), prob.data(), len.data(), n);
+    }
+    if (!in->pendingOps.empty()) {
+        std::vector<HostOp> hops;
+        hops.swap(in->pendingOps);
+        const int rc2 = planAndLaunch(in, hops, false);
+        if (rc == BEAGLE_SUCCESS) rc = rc2;
+    }
+    return rc;
+}
+
+bool fusionPossible(const Instance* in) {
+    return in->fuseSmall && in->matCP > 0 && in->matCP <= 8 && !in->timing && !in->exchangeOn && in->walkVariant == 0 &&
+           in->eigenWalk && in->hMapped != nullptr;
+}
+
+// the whole deferred evaluation as one launch; the caller has checked eligibility
+int launchFused(Instance* in, int E, int wIdx, int fIdx, int cum, double* outSum) {
+    IncArgs A;
+    memset(&A, 0, sizeof A);
+    A.partials = in->partialsBase; A.stride = in->partialsElems; A.states = in->states8Base; A.mats = in->dMat;
+    A.evecs = in->dEvec; A.scale = in->dScale; A.rates = in->dRates; A.matStride = in->matStride;
+    A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.P = in->P; A.logScalers = in->logScalers ? 1 : 0;
+    const double* h = in->hEigen.data() + (size_t)E * 36;
+    for (int q = 0; q < 16; ++q) { A.V[q] = h[q]; A.Vi[q] = h[16 + q]; }
+    for (int q = 0; q < 4; ++q) A.eval[q] = h[32 + q];
+    A.nMats = (int)in->pendingMats.size();
+    std::unordered_map<int, int> pendingOf;
+    for (int q = 0; q < A.nMats; ++q) {
+        A.mat[q] = IncMat{in->pendingMats[q].prob, in->pendingMats[q].rateSet, in->pendingMats[q].len};
+        pendingOf[in->pendingMats[q].prob] = q;
+    }
+    A.nOps = (int)in->pendingOps.size();
+    int prevDest = -1;
+    for (int k = 0; k < A.nOps; ++k) {
+        const HostOp& o = in->pendingOps[k];
+        IncOp& d = A.op[k];
+        const bool t1 = in->states32[o.c1] != nullptr, t2 = in->states32[o.c2] != nullptr;
+        int c1 = o.c1, c2 = o.c2, m1 = o.m1, m2 = o.m2;
+        d.flags = 0;
+        if (k > 0 && !t1 && c1 == prevDest) d.flags = 1;
+        else if (k > 0 && !t2 && c2 == prevDest) { std::swap(c1, c2); std::swap(m1, m2); d.flags = 1; }
+        const bool s1 = in->states32[c1] != nullptr, s2 = in->states32[c2] != nullptr;
+        d.dest = in->slotOf[o.dest];
+        d.c1 = s1 ? -(c1 + 1) : in->slotOf[c1];
+        d.c2 = s2 ? -(c2 + 1) : in->slotOf[c2];
+        auto mat = [&](int m) { auto it = pendingOf.find(m); return it == pendingOf.end() ? m : -(it->second + 1); };
+        d.m1 = mat(m1); d.m2 = mat(m2);
+        d.sw = o.sw; d.sr = o.sw >= 0 ? -1 : o.sr;
+        prevDest = o.dest;
+    }
+    A.weights = in->dWeights + (size_t)wIdx * in->C;
+    A.freqs = in->dFreqs + (size_t)fIdx * in->Sp;
+    A.cum = cum == BEAGLE_OP_NONE ? nullptr : in->dScale + (size_t)cum * in->Ppad;
+    A.patternWeights = in->dPatternWeights; A.site = in->dSite; A.blockSums = in->dIncSums; A.counter = in->dIncCounter;
+    A.out = in->dOut;
+    A.hostOut = in->dMapped;
+    A.hostFlag = reinterpret_cast<volatile unsigned long long*>(in->dMapped + 1);
+    A.seq = ++in->incSeq;
+    CUDA_OK(launchIncremental(in, A));
+    noteScaleWrites(in, in->pendingOps);
+    in->pendingMats.clear();
+    in->pendingOps.clear();
+    in->fusedLaunches++;
+    // the result lands in mapped pinned memory: spin on the flag (bounded), no memcpy, no stream synchronise
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(in->hMapped + 1);
+    const auto t0 = std::chrono::steady_clock::now();
+    long spins = 0;
+    while (*flag != A.seq) {
+        if ((++spins & 0xfff) == 0 &&
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 5.0) {
+            CUDA_OK(cudaStreamSynchronize(in->stream));       // a wedged device surfaces as an error here
+            if (*flag != A.seq) return BEAGLE_ERROR_GENERAL;
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *outSum = in->hMapped[0];
+    return std::isnan(*outSum) ? BEAGLE_ERROR_FLOATING_POINT : BEAGLE_SUCCESS;
+}
+int flushPending(Instance* in) { return flushPendingImpl(in); }
+}  // namespace
+extern "C" {
+
 int beagleUpdateTransitionMatrices(int instance, int eigenIndex, const int* probabilityIndices,
                                    const int* firstDerivativeIndices, const int* secondDerivativeIndices,
                                    const double* edgeLengths, int count) {
     SH(instance, shBroadcast(sh, [&](int c) { return beagleUpdateTransitionMatrices(c, eigenIndex, probabilityIndices, firstDerivativeIndices, secondDerivativeIndices, edgeLengths, count); }));
-    GET_INSTANCE(in, instance);
+    GET_INSTANCE_LAZY(in, instance);
     if (firstDerivativeIndices != nullptr || secondDerivativeIndices != nullptr)
         return BEAGLE_ERROR_NO_IMPLEMENTATION;      // derivative matrices: SURVEY.md 8f "next"
+    // a few branches of a real eigen system, nothing else pending: keep them for the one-launch evaluation (incr.cu)
+    bool defer = fusionPossible(in) && count >= 1 && in->pendingOps.empty() &&
+                 (int)in->pendingMats.size() + count <= kIncMaxMats && validRange(eigenIndex, in->nEigen) &&
+                 in->eigenReal[eigenIndex] && in->eigenGen[eigenIndex] > 0;
+    for (int k = 0; k < count && defer; ++k) {
+        defer = validRange(probabilityIndices[k], in->nMatrices);
+        for (const Instance::PendingMat& pm : in->pendingMats) defer = defer && pm.prob != probabilityIndices[k] && pm.eigen == eigenIndex;
+        for (int q = 0; q < k && defer; ++q) defer = probabilityIndices[q] != probabilityIndices[k];
+    }
+    if (defer) {
+        for (int k = 0; k < count; ++k) {
+            in->pendingMats.push_back(Instance::PendingMat{probabilityIndices[k], eigenIndex, 0, edgeLengths[k]});
+            in->matEigen[probabilityIndices[k]] = eigenIndex;
+            in->matEigenGen[probabilityIndices[k]] = in->eigenGen[eigenIndex];
+        }
+        return BEAGLE_SUCCESS;
+    }
+    if (!in->pendingMats.empty() || !in->pendingOps.empty()) { const int rc = flushPending(in); if (rc != BEAGLE_SUCCESS) return rc; }
     return updateMatricesImpl(in, nullptr, eigenIndex, nullptr, probabilityIndices, edgeLengths, count);
 }
 
@@ -1481,7 +1633,7 @@ int beagleTransposeTransitionMatrices(int instance, const int* inputIndices, con
 int beagleUpdatePartials(int instance, const BeagleOperation* operations, int operationCount,
                          int cumulativeScaleIndex) {
     SH(instance, shBroadcast(sh, [&](int c) { return beagleUpdatePartials(c, operations, operationCount, cumulativeScaleIndex); }));
-    GET_INSTANCE(in, instance);
+    GET_INSTANCE_LAZY(in, instance);
     if (operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
     std::vector<HostOp> hops(operationCount);
     for (int k = 0; k < operationCount; ++k) {
@@ -1489,6 +1641,22 @@ int beagleUpdatePartials(int instance, const BeagleOperation* operations, int op
         hops[k] = {o.destinationPartials, o.destinationScaleWrite, o.destinationScaleRead, o.child1Partials,
                    o.child1TransitionMatrix, o.child2Partials, o.child2TransitionMatrix, 0, cumulativeScaleIndex};
     }
+    // a short list in eigen form: hold it back, calculateRootLogLikelihoods will run matrices + list + root as ONE launch
+    if (fusionPossible(in) && operationCount >= 1 && operationCount <= kIncMaxOps && in->pendingOps.empty() &&
+        cumulativeScaleIndex == BEAGLE_OP_NONE) {
+        bool ok = true;
+        for (const HostOp& o : hops)
+            ok = ok && validRange(o.m1, in->nMatrices) && validRange(o.m2, in->nMatrices);
+        const int E = ok ? eigenFormSlot(in, hops) : -1;
+        for (const Instance::PendingMat& pm : in->pendingMats) ok = ok && pm.eigen == E;
+        if (ok && E >= 0) {
+            const int rc = prepareOps(in, hops, false);
+            if (rc != BEAGLE_SUCCESS) return rc;
+            in->pendingOps = hops;
+            return BEAGLE_SUCCESS;
+        }
+    }
+    if (!in->pendingMats.empty() || !in->pendingOps.empty()) { const int rc = flushPending(in); if (rc != BEAGLE_SUCCESS) return rc; }
     return planAndLaunch(in, hops, false);
 }
 
@@ -1659,7 +1827,16 @@ int beagleCalculateRootLogLikelihoods(int instance, const int* bufferIndices, co
                                       const int* stateFrequenciesIndices, const int* cumulativeScaleIndices,
                                       int count, double* outSumLogLikelihood) {
     SH(instance, shRoot(sh, bufferIndices, categoryWeightsIndices, stateFrequenciesIndices, cumulativeScaleIndices, count, outSumLogLikelihood));
-    GET_INSTANCE(in, instance);
+    GET_INSTANCE_LAZY(in, instance);
+    if (!in->pendingOps.empty() && count == 1 && fusionPossible(in) && bufferIndices[0] == in->pendingOps.back().dest &&
+        validRange(categoryWeightsIndices[0], in->nSets) && validRange(stateFrequenciesIndices[0], in->nSets) &&
+        (cumulativeScaleIndices[0] == BEAGLE_OP_NONE || validRange(cumulativeScaleIndices[0], in->nScale))) {
+        const int E = eigenFormSlot(in, in->pendingOps);
+        if (E >= 0)
+            return launchFused(in, E, categoryWeightsIndices[0], stateFrequenciesIndices[0], cumulativeScaleIndices[0],
+                               outSumLogLikelihood);
+    }
+    if (!in->pendingMats.empty() || !in->pendingOps.empty()) { const int rc = flushPending(in); if (rc != BEAGLE_SUCCESS) return rc; }
     if (count != 1) return BEAGLE_ERROR_NO_IMPLEMENTATION;   // BEAST always passes 1 (BDLD:934-935)
     int rc = rootLaunch(in, bufferIndices[0], categoryWeightsIndices[0], stateFrequenciesIndices[0],
                         cumulativeScaleIndices[0], 0, in->P, in->dOut, true);
@@ -2010,6 +2187,12 @@ int b200SetShardDevices(const int* devices, int count) {
     std::lock_guard<std::mutex> lock(gMutex);
     gShardDevices.assign(devices, devices + count);
     return BEAGLE_SUCCESS;
+}
+
+// how many evaluations of this instance ran as ONE fused launch (incr.cu); -1 for an unknown instance
+long b200GetFusedLaunches(int instance) {
+    Instance* in = getInstance(instance);
+    return in == nullptr ? -1 : in->fusedLaunches;
 }
 
 void* b200HostAlloc(long bytes) {

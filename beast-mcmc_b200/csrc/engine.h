@@ -78,6 +78,23 @@ struct CachedPlan {
 
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
 
+// ---- deferred small evaluations (incr.cu): a short updateTransitionMatrices -> updatePartials -> root sequence as ONE
+// launch, all of its arguments by value in the kernel parameters
+constexpr int kIncMaxOps = 64, kIncMaxMats = 8;
+struct IncOp { int dest, c1, c2, m1, m2, sw, sr, flags; };      // m < 0: pending branch -(q+1); flags bit 0: c1 = previous result
+struct IncMat { int prob, rateSet; double len; };
+struct IncArgs {
+    double* partials; size_t stride; const uint8_t* states; double* mats; double* evecs; double* scale; const double* rates;
+    size_t matStride;
+    int S, C, Ppad, P, logScalers, nOps, nMats, pad_;
+    double V[16], Vi[16], eval[4];
+    const double* weights; const double* freqs; const double* cum; const double* patternWeights;
+    double* site; double* blockSums; unsigned int* counter; double* out;
+    volatile double* hostOut; volatile unsigned long long* hostFlag; unsigned long long seq;
+    IncMat mat[kIncMaxMats];
+    IncOp op[kIncMaxOps];
+};
+
 // ---- cross-GPU sum of the per-shard log-likelihoods, fused into k_root (no NCCL launch, no host in the loop) -------------
 // Every member of a reduce group owns [2 banks][size] slots in ITS device memory; all members map all members' slots
 // (peer access inside a process, CUDA IPC across processes).  The finishing block of k_root stores {local sum, sequence
@@ -156,6 +173,19 @@ struct Instance {
     size_t stageSize = 0, stagePos = 0;
     double* hOut = nullptr;                   // pinned result landing zone
 
+    // deferred small evaluations (incr.cu): what updateTransitionMatrices / updatePartials have accepted but not launched yet
+    int fuseSmall = 1;                        // B200_FUSE
+    struct PendingMat { int prob, eigen, rateSet; double len; };
+    std::vector<PendingMat> pendingMats;
+    std::vector<HostOp> pendingOps;
+    int pendingCum = -1;
+    double* hMapped = nullptr;                // mapped pinned: [0] = value, [1] = sequence flag (as u64)
+    double* dMapped = nullptr;                // its device alias
+    double* dIncSums = nullptr;               // per-block partial sums of k_incremental
+    unsigned int* dIncCounter = nullptr;
+    unsigned long long incSeq = 0;
+    long fusedLaunches = 0;
+
     void* shard = nullptr;                    // non-null: this id is a pattern-sharded instance over several GPUs (multi.cu)
     // reduce group (b200Exchange*): set up once, used by every single-root launch from then on
     Exchange exchange;
@@ -221,6 +251,7 @@ cudaError_t launchCrossProducts(Instance* in, const EdgeRef* dEdges, int count, 
 // exchange: non-null = add the other members' sums inside the kernel (dOutSlot[0] = joint value, dOutSlot[1] = local)
 cudaError_t launchRoot(Instance* in, const double* root, const double* weights, const double* freqs,
                        const double* cumScale, int pBegin, int pEnd, double* dOutSlot, const Exchange* exchange = nullptr);
+cudaError_t launchIncremental(Instance* in, const IncArgs& args);
 cudaError_t launchCombineMatrices(Instance* in, const int* dFirst, const int* dSecond, const int* dResult, int count, bool multiply);
 cudaError_t launchExchangeSum(Instance* in, const double* dVals, int n, double* dOutJoint, const Exchange* exchange);
 cudaError_t launchScaleAccumulate(Instance* in, const int* dIdx, int count, double* cum, double sign,

@@ -315,6 +315,12 @@ BEAGLE_DLLEXPORT int b200GetKernelTiming(int instance, int which, double* outMil
  * beast-mcmc_b200/build.py compare it with the tree so that a prebuilt library cannot drift from its sources.  The same
  * string is the build-metadata suffix of beagleGetVersion ("4.0.1-b200+<hash>"). */
 BEAGLE_DLLEXPORT const char* b200GetSourceHash(void);
+/* Deferred small evaluations (csrc/incr.cu): on 4-state instances a short beagleUpdateTransitionMatrices (<= 8 branches) ->
+ * beagleUpdatePartials (<= 64 operations) -> beagleCalculateRootLogLikelihoods sequence -- what an MCMC move that dirties
+ * one root path issues (MarkovChain.java:207-393) -- is executed as ONE kernel launch at the root call, its result written
+ * to mapped pinned host memory; any other entry point first launches what was deferred, so the calls keep their upstream
+ * meaning.  B200_FUSE=0 (environment) switches the deferral off.  This counter reports how often it happened. */
+BEAGLE_DLLEXPORT long b200GetFusedLaunches(int instance);
 /* Pinned-host staging for callers that want the H2D/D2H copies to be asynchronous. */
 BEAGLE_DLLEXPORT void* b200HostAlloc(long bytes);
 BEAGLE_DLLEXPORT void b200HostFree(void* p);
