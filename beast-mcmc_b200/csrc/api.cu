@@ -802,6 +802,12 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             }
         }
     }
+    if (fourPath && getenv("B200_BEAGLE_DEBUG")) {
+        int fwd = 0, internal = 0;
+        for (const Op4& d : ops4) { fwd += (d.pad_ & 2) != 0; internal += (d.c1 >= 0) + (d.c2 >= 0); }
+        fprintf(stderr, "[b200-beagle] plan: %d ops, %zu subtrees, %d phases, %d internal children, %d forwarded in registers\n",
+                n, plan.subs.size(), nPhases, internal, fwd);
+    }
     const void* hostOps = fourPath ? (const void*)ops4.data() : (const void*)dops.data();
     const size_t opBytes = (fourPath ? sizeof(Op4) : sizeof(DevOp)) * (size_t)n;
     const size_t subBytes = sizeof(Sub) * plan.subs.size();
@@ -1002,6 +1008,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->phaseSmall = envInt("B200_PHASE_SMALL", 24);
     in->phaseOversub = std::max(0, envInt("B200_PHASE_OVERSUB", 0));      // 0 = by subtree width (see wantSubsFor)
     in->walkMinBlocks = envInt("B200_WALK_MINB", 4);
+    in->walkMinBlocksSet = getenv("B200_WALK_MINB") != nullptr;
     in->tensorR = envInt("B200_TENSOR_R", 2) >= 4 ? 4 : 2;
     in->genericMma = envInt("B200_GENERIC_MMA", 1);
     in->mmaWarps = envInt("B200_MMA_WARPS", 4) == 8 ? 8 : 4;     // 8 = 256-thread blocks with cp.async double buffering

@@ -212,6 +212,7 @@ struct Instance {
     int stackTail = 0;           // operand stack for latency-bound (thin) phases of the 4-state walk (experiment, off)
     int stackDepthMax = 12;
     int walkMinBlocks = 4;       // __launch_bounds__(128, n) variant of the 4-state walk (4, 5 or 6)
+    bool walkMinBlocksSet = false;   // B200_WALK_MINB given explicitly
     int mmaWarps = 4;            // codon-size tensor walk: 4 warps single-buffered (default) or 8 warps double-buffered
     int tensorR = 2;             // 8-pattern tiles per warp in the 4-state tensor walk (2 or 4)
     int genericMma = 1;          // S > 4: 1 = fp64 tensor-core block walk, 0 = FMA block walk

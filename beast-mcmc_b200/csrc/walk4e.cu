@@ -277,10 +277,15 @@ k_walk4p(const WalkArgs A) {
         const int tbl = q / (CP * 4), e = q % (CP * 4);
         stage[tbl >> 1].mat[tbl & 1][4 * CP * 4 + e] = ((e & 3) < S) ? 1.0 : 0.0;
     }
-    // what op j reads beyond partials goes to stage j & 1; reads record j from the ring (it has arrived)
-    auto issueOperands = [&](int j) {
+    // what op j reads beyond partials goes to stage j & 1; reads record j from the ring (it has arrived) ONCE -- the fields
+    // the compute part needs travel on in registers (4 shared-memory reads per op instead of 20)
+    struct Rec { int dest, c1, c2, sw, sr, flags, pfA, pfB; };
+    auto issueOperands = [&](int j) -> Rec {
         const int4 rec = *reinterpret_cast<const int4*>(&ring[j & 3]);          // dest, c1, c2, m1
-        const int m2 = ring[j & 3].m2;
+        const int4 rec2 = *(reinterpret_cast<const int4*>(&ring[j & 3]) + 1);   // m2, sw, sr, cum
+        const int flags = ring[j & 3].pad_;
+        const int2 pf = *reinterpret_cast<const int2*>(&ring[j & 3].pfA);
+        const int m2 = rec2.x;
         WarpStage<CP, R>& sg = stage[j & 1];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -305,6 +310,7 @@ k_walk4p(const WalkArgs A) {
                 cpAsync16(&sg.st[ch][16 * piece], A.states + (size_t)(-child - 1) * A.Ppad + pBase + 16 * piece);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        return Rec{rec.x, rec.y, rec.z, rec2.y, rec2.z, flags, pf.x, pf.y};
     };
     // prologue: records k0 (and k0+1 through issueOperands), then the operands of k0
     if (lane < 4) cpAsync16(reinterpret_cast<char*>(&ring[range.x & 3]) + 16 * lane,
@@ -312,7 +318,7 @@ k_walk4p(const WalkArgs A) {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    issueOperands(range.x);
+    Rec nxt = issueOperands(range.x);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 
@@ -324,8 +330,8 @@ k_walk4p(const WalkArgs A) {
     for (int r = 0; r < R; ++r) d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.0;
 
     for (int k = range.x; k <= last; ++k) {
-        if (k + 1 <= last) issueOperands(k + 1);                   // travels while op k computes
-        const Op4 cur = ring[k & 3];
+        const Rec cur = nxt;
+        if (k + 1 <= last) nxt = issueOperands(k + 1);             // travels while op k computes
         const WarpStage<CP, R>& sg = stage[k & 1];
         // look-ahead for the child partials of op k+1 that are not forwarded (never this op's destination)
 #pragma unroll
@@ -352,7 +358,7 @@ k_walk4p(const WalkArgs A) {
                 const double2* ep = reinterpret_cast<const double2*>(&sg.ev[ch][cc * 4]);
                 const double2 e01 = ep[0], e23 = ep[1];
                 const double e[4] = {e01.x, e01.y, e23.x, e23.y};
-                const bool fromRegisters = ch == 0 && (cur.pad_ & 2) != 0;
+                const bool fromRegisters = ch == 0 && (cur.flags & 2) != 0;
                 const double* xg = A.partials + (size_t)child * A.stride + off0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -427,7 +433,9 @@ cudaError_t launchR(Instance* in, WalkArgs& A, int nSubs, int maxWindow, bool al
     if constexpr (CP <= 8 && (G * R) % 16 == 0) {
         if (in->tipMode == 3) {                 // per-warp asynchronous operand staging (k_walk4p)
             if constexpr (CP == 4) {
-                const int minb = in->walkMinBlocks;
+                // measured (profiles/r02_sweep_cfg2.txt): a launch bound of 3 blocks lets ptxas keep 120 registers without a
+                // spill and 4 blocks still fit -- the fastest setting unless B200_WALK_MINB says otherwise
+                const int minb = in->walkMinBlocksSet ? in->walkMinBlocks : 3;
                 if (minb >= 6) return launchP<CP, R, 6>(in, A, grid);
                 if (minb == 5) return launchP<CP, R, 5>(in, A, grid);
                 if (minb == 3) return launchP<CP, R, 3>(in, A, grid);
