@@ -72,6 +72,23 @@ k_incremental(const IncArgs A) {
     const bool inRange = p < A.Ppad;
     const int pp = inRange ? p : 0;
     const size_t off0 = ((size_t)cc * A.Ppad + pp) * 4;
+    // everything the chain will read from memory is known up front (the list is in the kernel parameters): start all of it
+    // on its way to L1 now, so that the dependent chain below runs at cache-hit latency instead of one L2 round trip per op
+    for (int k = 0; k < A.nOps; ++k) {
+        const IncOp op = A.op[k];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int child = ch == 0 ? op.c1 : op.c2, m = ch == 0 ? op.m1 : op.m2;
+            if (child < 0) {
+                if (c == 0) prefetchL1(A.states + (size_t)(-child - 1) * A.Ppad + pp);
+                if (m >= 0 && lane < 4) prefetchL1(A.mats + (size_t)m * A.matStride + lane * 4 * CP);
+            } else {
+                if (!(ch == 0 && (op.flags & 1)) && catValid) prefetchL1(A.partials + (size_t)child * A.stride + off0);
+                if (m >= 0 && lane == 0) prefetchL1(A.evecs + (size_t)m * CP * 4);
+            }
+        }
+        if (op.sr >= 0 && c == 0) prefetchL1(A.scale + (size_t)op.sr * A.Ppad + pp);
+    }
     double d[4] = {0.0, 0.0, 0.0, 0.0};
     for (int k = 0; k < A.nOps; ++k) {
         const IncOp op = A.op[k];

@@ -1018,7 +1018,34 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                         acc[m][n][e] = child == 0 ? cur[m][n][e] : acc[m][n][e] * cur[m][n][e];
         }
         }
-        // store the (unscaled) tile: lane (g,t) owns states 8n+2t, 8n+2t+1 of rows g and g+8
+        // one category (the codon workloads): the per-pattern factor is known before anything is stored -- scale the
+        // accumulators in registers and write the tile ONCE (the general path below re-reads and re-writes C tiles)
+        const bool scaleInRegisters = C == 1 && (op.scaleWrite != nullptr || op.scaleRead != nullptr);
+        if (scaleInRegisters) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int p = pw + 8 * m + g;
+                double f;
+                if (op.scaleWrite != nullptr) {
+                    double mx = 0.0;
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) mx = fmax(mx, fmax(acc[m][n][0], acc[m][n][1]));
+                    if (!act[m]) mx = 0.0;
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    if (mx == 0.0) mx = 1.0;
+                    f = mx;
+                    if (act[m] && t == 0) op.scaleWrite[p] = logScalers ? log(mx) : mx;
+                } else {
+                    f = act[m] ? op.scaleRead[p] : 1.0;
+                    if (logScalers) f = exp(f);
+                }
+                const double inv = 1.0 / f;
+#pragma unroll
+                for (int n = 0; n < NT; ++n) { acc[m][n][0] *= inv; acc[m][n][1] *= inv; }
+            }
+        }
+        // store the tile: lane (g,t) owns states 8n+2t, 8n+2t+1 of rows g and g+8
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             if (!act[m]) continue;
@@ -1029,7 +1056,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 rowMax[m] = fmax(rowMax[m], fmax(acc[m][n][0], acc[m][n][1]));
             }
         }
-        if (c == C - 1 && (op.scaleWrite != nullptr || op.scaleRead != nullptr)) {
+        if (c == C - 1 && !scaleInRegisters && (op.scaleWrite != nullptr || op.scaleRead != nullptr)) {
             // per-pattern factor (max over categories and states), then one more pass over what this
             // warp just wrote (same lanes re-read their own stores)
 #pragma unroll

@@ -235,10 +235,15 @@ k_walk4e(const WalkArgs A) {
 //                      ev[child][CP][4]      spectrum of an internal child
 //                      st[child][G*R]        state bytes of a tip child for this warp's patterns
 // Child partials that are not forwarded in registers keep the look-ahead L1 prefetch.  Aligned lists only (every op spans
-// [0, Ppad), a warp's G*R patterns start at a multiple of 16): windows and thin R = 1 phases use k_walk4e.
+// [0, Ppad)), thin R = 1 phases included; pattern windows (by-partition lists) use k_walk4e.
 __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
     const unsigned sAddr = (unsigned)__cvta_generic_to_shared(smemDst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sAddr), "l"(gmemSrc) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cpAsyncSmall(void* smemDst, const void* gmemSrc) {      // 4, 8 or 16 bytes
+    const unsigned sAddr = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" :: "r"(sAddr), "l"(gmemSrc), "n"(BYTES) : "memory");
 }
 
 template <int CP, int R>
@@ -246,14 +251,15 @@ struct WarpStage {
     static constexpr int G = 32 / CP, NP = G * R;
     double mat[2][5 * CP * 4];
     double ev[2][CP * 4];
-    unsigned char st[2][NP];
+    alignas(16) unsigned char st[2][NP < 16 ? 16 : NP];
 };
 
 template <int CP, int R, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_walk4p(const WalkArgs A) {
     constexpr int G = 32 / CP, NP = G * R;
-    static_assert(NP % 16 == 0, "state bytes are staged in 16-byte pieces");
+    constexpr int PIECE = NP < 16 ? NP : 16;                       // state bytes travel in 4-, 8- or 16-byte pieces
+    static_assert(NP % PIECE == 0 && (PIECE == 4 || PIECE == 8 || PIECE == 16), "state-byte staging");
     __shared__ __align__(16) WarpStage<CP, R> stages[4][2];
     __shared__ __align__(16) Op4 rings[4][4];
     int lane;
@@ -299,7 +305,7 @@ k_walk4p(const WalkArgs A) {
             }
         }
         // one more instruction: state bytes of the tip children (lanes 4 ..) and, on lanes 0-3, record j + 1
-        constexpr int SL = NP / 16;
+        constexpr int SL = NP / PIECE;
         if (lane < 4) {
             if (j + 1 <= last) cpAsync16(reinterpret_cast<char*>(&ring[(j + 1) & 3]) + 16 * lane,
                                          reinterpret_cast<const char*>(A.ops + j + 1) + 16 * lane);
@@ -307,7 +313,7 @@ k_walk4p(const WalkArgs A) {
             const int ch = (lane - 4) / SL, piece = (lane - 4) % SL;
             const int child = ch == 0 ? rec.y : rec.z;
             if (child < 0)
-                cpAsync16(&sg.st[ch][16 * piece], A.states + (size_t)(-child - 1) * A.Ppad + pBase + 16 * piece);
+                cpAsyncSmall<PIECE>(&sg.st[ch][PIECE * piece], A.states + (size_t)(-child - 1) * A.Ppad + pBase + PIECE * piece);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         return Rec{rec.x, rec.y, rec.z, rec2.y, rec2.z, flags, pf.x, pf.y};
@@ -430,7 +436,7 @@ cudaError_t launchR(Instance* in, WalkArgs& A, int nSubs, int maxWindow, bool al
     dim3 grid((warps + 3) / 4, nSubs);
     // predicate-free only when a warp's G*R patterns can never straddle the end of the padded pattern axis
     if (!aligned || in->Ppad % (G * R) != 0) return launchK<CP, R, false, 4, TIPD>(in, A, grid);
-    if constexpr (CP <= 8 && (G * R) % 16 == 0) {
+    if constexpr (CP <= 8 && G * R >= 4) {
         if (in->tipMode == 3) {                 // per-warp asynchronous operand staging (k_walk4p)
             if constexpr (CP == 4) {
                 // measured (profiles/r02_sweep_cfg2.txt): a launch bound of 3 blocks lets ptxas keep 120 registers without a

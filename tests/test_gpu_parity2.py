@@ -546,7 +546,9 @@ def test_fused_incremental_evaluations_match_oracle(cats, scheme):
     vg, sg, fused = walk(GPU, [1, 0], "1")
     vp, sp, plain = walk(GPU, [1, 0], "0")
     vo, so, _ = walk(ORACLE, None, "1")
-    assert fused >= 25 and plain == 0, (fused, plain)
+    # ALWAYS resets and accumulates the scale factors between the list and the root call: such evaluations keep the ordinary
+    # launches; NONE and DYNAMIC (scale factors only READ by the ops, BEAST's default) fuse
+    assert plain == 0 and (fused == 0 if scheme == S_.ALWAYS else fused >= 25), (fused, plain)
     assert all(math.isfinite(v) for v in vo)
     assert all(_rel(a, b) <= REL for a, b in zip(vg, vo)), max(_rel(a, b) for a, b in zip(vg, vo))
     assert all(_rel(a, b) <= 1e-13 for a, b in zip(vg, vp))
