@@ -142,7 +142,7 @@ def test_reduce_group_of_plain_instances_from_threads():
     b200ExchangeConnectLocal, each driven from its own thread -- every member's calculateRootLogLikelihoods returns the
     JOINT value, bit-equal to the host-side sum in shard order.  Distinct devices when the box has them."""
     g = 4
-    tree, pats, model, site = H.synthetic_case(50, 2003, 4, seed=3)
+    tree, pats, model, site = H.synthetic_case(100, 2003, 4, seed=3)      # > 64 operations: the ordinary launches on both sides
     devices = _devices(g)
     shards = [pats.subSet(k, g) for k in range(g)]
     plain = []

@@ -504,7 +504,7 @@ def test_plan_cache_hits_and_invalidation():
     """Identical op lists are served from the plan cache; a buffer changing kind (setTipStates / setPartials on a tip)
     or different lists must not be.  Every value equals the cache-less engine."""
     import os
-    tree, pats, model, site = H.synthetic_case(40, 300, 4, seed=77)
+    tree, pats, model, site = H.synthetic_case(90, 300, 4, seed=77)      # > 64 operations: planned lists, not the fused route
 
     def run(cache, graphs="1"):
         os.environ["B200_PLAN_CACHE"] = cache
