@@ -126,8 +126,21 @@ def build_oracle(force=False, verbose=False):
     return out
 
 
+def build_cdriver(force=False, verbose=False):
+    """bench infrastructure (harness/cdriver.c): replays prepared C-ABI call sequences from C, as a JVM's JNI thread would."""
+    src = os.path.join(ROOT, "harness", "cdriver.c")
+    if not os.path.exists(src):
+        return None
+    out = os.path.join(ROOT, "harness", "libcdriver.so")
+    if force or _stale(out, [src, os.path.join(ROOT, "include", "libhmsbeagle_b200.h"), lib_path()]):
+        _run(["gcc", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", out, src, "-L", CSRC, "-lhmsbeagle",
+              "-Wl,-rpath,$ORIGIN/../beast-mcmc_b200/csrc"], verbose)
+    return out
+
+
 def build_all(force=False, verbose=False):
-    return build_engine(force, verbose), build_jni(force, verbose), build_oracle(force, verbose)
+    return (build_engine(force, verbose), build_jni(force, verbose), build_oracle(force, verbose),
+            build_cdriver(force, verbose))
 
 
 if __name__ == "__main__":

@@ -773,6 +773,17 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             d.pBegin = pBegin; d.pEnd = pEnd;
             d.srcSlot1 = d.srcSlot2 = d.dstSlot = -1;
             d.pad_ = o.kind;
+            // register forwarding on the tensor-pipe walk (one category): the warp that wrote the previous op's 16-pattern
+            // tile still holds it in its accumulators -- flag the child (moved to position 1; the product commutes exactly)
+            if (in->forward && !preOrder && pos > plan.subs[subOfPos[pos]].begin) {
+                const DevOp& pv = dops[pos - 1];
+                if (pv.pBegin == d.pBegin && pv.pEnd == d.pEnd) {
+                    if (d.c1 != nullptr && d.c1 == pv.dest) d.pad_ |= 2;
+                    else if (d.c2 != nullptr && d.c2 == pv.dest) {
+                        std::swap(d.c1, d.c2); std::swap(d.s1, d.s2); std::swap(d.m1, d.m2); d.pad_ |= 2;
+                    }
+                }
+            }
         }
     }
     if (fourPath && in->lookahead && (!preOrder || in->lookaheadPre)) {

@@ -691,7 +691,7 @@ k_walk_generic(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int
         if (doMax) for (int q = tid; q < TP; q += nt) pmax[q] = 0ull;
         for (int c = 0; c < C; ++c) {
             __syncthreads();
-            const bool pre = op.pad_ == 1;
+            const bool pre = (op.pad_ & 1) != 0;
             // pre-order ops use the ROW-MAJOR copy of the node's own matrix (second half of the buffer)
             const int ld1 = pre ? Sp + 4 : Sp;       // the row-major copy carries the tensor path's padded row stride
             const double* m1g = op.m1 + (pre ? (size_t)C * Sp * Sp + (size_t)c * Sp * ld1 : (size_t)c * Sp * Sp);
@@ -869,6 +869,13 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
 
     bool act[2] = {false, false};
     double rowMax[2] = {0.0, 0.0};
+    // the accumulator tile outlives the iteration: with one category the next op of the walk may take it as its first
+    // child straight from these registers (DevOp::pad_ bit 1, set by the planner as for the 4-state walk)
+    double acc[2][NT][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
     for (int flat = 0; flat < total; ++flat) {
         const int c = flat % C, cg = c % cb;
         if (cg == 0) {
@@ -876,8 +883,10 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 const DevOp* o = ops + range.x + flat / C;
                 const unsigned bytes = (unsigned)min(cb, C - c) * MATBYTES;       // consecutive categories are contiguous
                 // pre-order ops contract over the ROW index of the node's own matrix: stage its transposed copy
-                const double* g1 = o->m1 + (PRE ? mTp : mRow) + (size_t)c * MATSZ;
-                const double* g2 = o->m2 + mRow + (size_t)c * MATSZ;
+                // a compact-tip child of a post-order op only needs COLUMN s of its matrix: stage the transposed copy, where
+                // that column is one contiguous row (two LDS.128 per accumulator pair instead of bank-conflicting LDS.64s)
+                const double* g1 = o->m1 + ((PRE || o->c1 == nullptr) ? mTp : mRow) + (size_t)c * MATSZ;
+                const double* g2 = o->m2 + ((!PRE && o->c2 == nullptr) ? mTp : mRow) + (size_t)c * MATSZ;
                 // the generic-proxy reads of the previous group (ordered by the barrier that ended it) precede these writes
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbarExpectTx(&bar, 2 * bytes);
@@ -898,7 +907,6 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 rowMax[m] = 0.0;
             }
         }
-        double acc[2][NT][2];
         if constexpr (PRE) {
             // pre[node][j] = sum_i ( pre[parent][i] * (M_sib post[sib])[i] ) M_node[i][j]
             // (1) v = M_sib post[sib] on the tensor pipe (or a column lookup for a compact tip)
@@ -979,20 +987,42 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 for (int m = 0; m < 2; ++m)
 #pragma unroll
                     for (int n = 0; n < NT; ++n) { cur[m][n][0] = 0.0; cur[m][n][1] = 0.0; }
-                const double* xrow0 = xg + ((size_t)c * Ppad + (pw + g)) * Sp + t;
+                // The sum over the child's states j may visit them in any order, so k-chunk (n, e0) is DEFINED as the four
+                // states the lanes t = 0..3 hold in the ACCUMULATOR layout: j = 8n + 2t + (e0 ^ (t >> 1)).  The child tile is
+                // then read exactly as it was written (one 16-byte load per lane and state pair, half the instructions of the
+                // fragment-shaped 8-byte loads) -- or not read at all: when the child is the previous op's result, the
+                // A operands ARE the accumulator registers (no shuffle, no memory), with the same arithmetic either way.
+                const bool fwd = child == 0 && C == 1 && (op.pad_ & 2) != 0;
+                const int flip = t >> 1;
+                const double* xrow0 = xg + ((size_t)c * Ppad + (pw + g)) * Sp + 2 * t;
                 const double* xrow1 = xrow0 + (size_t)8 * Sp;
-                const double* brow = Ps + g * LD + t;
-#pragma unroll 4
-                for (int kc = 0; kc < Sp / 4; ++kc) {
-                    double a0 = 0.0, a1 = 0.0;
-                    if (act[0]) a0 = xrow0[4 * kc];
-                    if (act[1]) a1 = xrow1[4 * kc];
+                const double* brow = Ps + g * LD + 2 * t;
+                const bool ld0 = act[0] && !fwd, ld1 = act[1] && !fwd;
+                double2 x0 = make_double2(0.0, 0.0), x1 = make_double2(0.0, 0.0);
+                if (ld0) x0 = *reinterpret_cast<const double2*>(xrow0);
+                if (ld1) x1 = *reinterpret_cast<const double2*>(xrow1);
 #pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        const double b = brow[n * 8 * LD + 4 * kc];
-                        dmma884acc(cur[0][n][0], cur[0][n][1], a0, b);
-                        dmma884acc(cur[1][n][0], cur[1][n][1], a1, b);
+                for (int n = 0; n < NT; ++n) {
+                    double2 nx0 = make_double2(0.0, 0.0), nx1 = make_double2(0.0, 0.0);
+                    if (n + 1 < NT) {                                        // the next state pair travels while this one computes
+                        if (ld0) nx0 = *reinterpret_cast<const double2*>(xrow0 + 8 * (n + 1));
+                        if (ld1) nx1 = *reinterpret_cast<const double2*>(xrow1 + 8 * (n + 1));
                     }
+                    const double v00 = fwd ? acc[0][n][0] : x0.x, v01 = fwd ? acc[0][n][1] : x0.y;
+                    const double v10 = fwd ? acc[1][n][0] : x1.x, v11 = fwd ? acc[1][n][1] : x1.y;
+#pragma unroll
+                    for (int e0 = 0; e0 < 2; ++e0) {
+                        const int e = e0 ^ flip;
+                        const double a0 = e ? v01 : v00;
+                        const double a1 = e ? v11 : v10;
+#pragma unroll
+                        for (int n2 = 0; n2 < NT; ++n2) {
+                            const double b = brow[n2 * 8 * LD + 8 * n + e];
+                            dmma884acc(cur[0][n2][0], cur[0][n2][1], a0, b);
+                            dmma884acc(cur[1][n2][0], cur[1][n2][1], a1, b);
+                        }
+                    }
+                    x0 = nx0; x1 = nx1;
                 }
             } else {
                 const int* st = static_cast<const int*>(child == 0 ? op.s1 : op.s2);
@@ -1000,13 +1030,13 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 for (int m = 0; m < 2; ++m) {
                     const int p = pw + 8 * m + g;
                     const int s = act[m] ? st[p] : S;
+                    const double* col = Ps + (size_t)(s < S ? s : 0) * LD + 2 * t;      // staged TRANSPOSED: row s = column s of P
 #pragma unroll
-                    for (int n = 0; n < NT; ++n)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int i = 8 * n + 2 * t + e;
-                            cur[m][n][e] = (s < S) ? Ps[i * LD + s] : ((i < S) ? 1.0 : 0.0);
-                        }
+                    for (int n = 0; n < NT; ++n) {
+                        const double2 v = *reinterpret_cast<const double2*>(col + 8 * n);
+                        cur[m][n][0] = (s < S) ? v.x : ((8 * n + 2 * t < S) ? 1.0 : 0.0);
+                        cur[m][n][1] = (s < S) ? v.y : ((8 * n + 2 * t + 1 < S) ? 1.0 : 0.0);
+                    }
                 }
             }
 #pragma unroll

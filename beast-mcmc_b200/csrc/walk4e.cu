@@ -230,8 +230,14 @@ k_walk4e(const WalkArgs A) {
 // its own slice of shared memory: while op k computes, record k+2 and ALL small operands of op k+1 travel global -> shared
 // without touching a register; op k+1 finds them with shared-memory latency.  Per op and warp: three LDGSTS instructions.
 //   ring[4]            op records (64 B), fetched two ops ahead
-//   stage[k & 1]       mat[child][5][CP][4]  P block of a tip child exactly as it lies in HBM ([j][CP][i] = one contiguous
-//                                            copy), row 4 = the gap column (written once); a pattern picks its 32-B column
+//   stage[k & 1]       mat[child][2][5*CP][2] P block of a tip child: the contiguous [j][CP][i] block in HBM travels as 16-byte
+//                                            pieces, one per lane, and every piece lands where the READS are conflict-free:
+//                                            two half tables (states 0-1 / 2-3) of 16-byte entries indexed c*4 + j, so that
+//                                            the 8 lanes of a quarter warp (same category, 8 patterns) hit 4 distinct
+//                                            bank groups whatever their states -- with the HBM order kept ([j][c]: 128 B
+//                                            between states) they collided up to 4-way and 63 % of the kernel's shared-memory
+//                                            wavefronts were bank conflicts (profiles/r02_walk4e_summary.md).  Entries
+//                                            4*CP + c = the gap column (written once).  A pattern picks its column with two LDS.128
 //                      ev[child][CP][4]      spectrum of an internal child
 //                      st[child][G*R]        state bytes of a tip child for this warp's patterns
 // Child partials that are not forwarded in registers keep the look-ahead L1 prefetch.  Aligned lists only (every op spans
@@ -280,8 +286,8 @@ k_walk4p(const WalkArgs A) {
 
     // the gap column (row 4 of every table), once
     for (int q = lane; q < 4 * CP * 4; q += 32) {
-        const int tbl = q / (CP * 4), e = q % (CP * 4);
-        stage[tbl >> 1].mat[tbl & 1][4 * CP * 4 + e] = ((e & 3) < S) ? 1.0 : 0.0;
+        const int tbl = q / (CP * 4), e = q % (CP * 4), gc = e >> 2, i = e & 3;
+        stage[tbl >> 1].mat[tbl & 1][(i >> 1) * 10 * CP + 2 * (4 * CP + gc) + (i & 1)] = (i < S) ? 1.0 : 0.0;
     }
     // what op j reads beyond partials goes to stage j & 1; reads record j from the ring (it has arrived) ONCE -- the fields
     // the compute part needs travel on in registers (4 shared-memory reads per op instead of 20)
@@ -299,7 +305,8 @@ k_walk4p(const WalkArgs A) {
             if (child < 0) {
                 const double* src = A.mats + (size_t)m * A.matStride;          // [j][CP][i]: 4 * CP * 4 doubles, contiguous
 #pragma unroll
-                for (int q = lane; q < CP * 8; q += 32) cpAsync16(&sg.mat[ch][2 * q], src + 2 * q);
+                for (int q = lane; q < CP * 8; q += 32)                         // piece q = (j, c, half) -> half table, entry c*4 + j
+                    cpAsync16(&sg.mat[ch][(q & 1) * 10 * CP + 2 * (((q >> 1) % CP) * 4 + q / (2 * CP))], src + 2 * q);
             } else if (lane < CP * 2) {
                 cpAsync16(&sg.ev[ch][2 * lane], A.evecs + (size_t)m * CP * 4 + 2 * lane);
             }
@@ -355,8 +362,9 @@ k_walk4p(const WalkArgs A) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int sym = sg.st[ch][(lane % G) + r * G];
-                    const double2* col = reinterpret_cast<const double2*>(&sg.mat[ch][((sym < S ? sym : 4) * CP + cc) * 4]);
-                    const double2 lo = col[0], hi = col[1];
+                    const int e2 = 2 * (sym < S ? cc * 4 + sym : 4 * CP + cc);
+                    const double2 lo = *reinterpret_cast<const double2*>(&sg.mat[ch][e2]);
+                    const double2 hi = *reinterpret_cast<const double2*>(&sg.mat[ch][10 * CP + e2]);
                     if (ch == 0) { d[r][0] = lo.x; d[r][1] = lo.y; d[r][2] = hi.x; d[r][3] = hi.y; }
                     else { d[r][0] *= lo.x; d[r][1] *= lo.y; d[r][2] *= hi.x; d[r][3] *= hi.y; }
                 }

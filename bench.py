@@ -491,6 +491,41 @@ def measure_single_partition(D, lib, beagle, w, tree, pats, model, site, steps, 
     return res
 
 
+def replay_from_c(inst, paths, out):
+    """The same 64 evaluations issued from C (harness/cdriver.c) -- the three C-ABI calls per evaluation back to back, as a
+    JVM's JNI thread issues them, without the Python interpreter and ctypes marshalling between the calls."""
+    import ctypes as C
+    lib_file = os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness", "libcdriver.so")
+    if not os.path.exists(lib_file):
+        return None
+    drv = C.CDLL(lib_file)
+    ops = np.ascontiguousarray(np.concatenate([p[0] for p in paths]), dtype=np.int32)
+    opOff = np.concatenate([[0], np.cumsum([p[1] for p in paths])]).astype(np.int32)
+    matOff = np.arange(len(paths) + 1, dtype=np.int32)
+    probIdx = np.ascontiguousarray(np.concatenate([p[2] for p in paths]), dtype=np.int32)
+    lengths = np.ascontiguousarray(np.concatenate([p[3] for p in paths]), dtype=np.float64)
+    rootIdx = np.ascontiguousarray(np.concatenate([p[4] for p in paths]), dtype=np.int32)
+    rounds = 12
+    secs = np.zeros(rounds * len(paths))
+    last = C.c_double(0.0)
+    ptr = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    drv.cdriver_replay.restype = C.c_int
+    rc = drv.cdriver_replay(C.c_int(inst.instance), C.c_int(len(paths)), C.c_int(rounds), ptr(opOff, C.c_int), ptr(ops, C.c_int),
+                            ptr(matOff, C.c_int), ptr(probIdx, C.c_int), ptr(lengths, C.c_double), ptr(rootIdx, C.c_int),
+                            C.c_int(0), C.c_int(-1), ptr(secs, C.c_double), C.byref(last))
+    if rc != 0:
+        return {"error": rc}
+    per = sorted(secs[2 * len(paths):])                        # two warm-up rounds
+    expect = np.zeros(1)
+    o, cnt, pidx, blen, ridx = paths[-1]
+    inst.updateTransitionMatrices(0, pidx, None, None, blen, 1)
+    inst.updatePartials(o, cnt, -1)
+    inst.calculateRootLogLikelihoods(ridx, ZERO, ZERO, MINUS1, 1, expect)
+    return {"us_per_eval": 1e6 * per[len(per) // 2], "us_p10": 1e6 * per[len(per) // 10], "us_p90": 1e6 * per[(9 * len(per)) // 10],
+            "evals_per_s": 1.0 / per[len(per) // 2], "same_value_as_python_calls": bool(expect[0] == last.value),
+            "what": "the same evaluations, the three C-ABI calls issued from C (harness/cdriver.c): no interpreter between calls"}
+
+
 def incremental_section(inst, ev, tree, out, steps):
     """The evaluation MCMC mostly issues: one branch length changed -> 1 matrix, the tip-to-root path of ops, root."""
     issue_sync(inst, ev, 0, out)                       # parity-0 buffers hold the current state
@@ -531,6 +566,7 @@ def incremental_section(inst, ev, tree, out, steps):
     inc = {"evals_per_s": 1.0 / statistics.median(per), "us_per_eval": 1e6 * statistics.median(per),
            "us_p10": 1e6 * _quantiles(per)[0], "us_p90": 1e6 * _quantiles(per)[2],
            "mean_ops_per_eval": float(np.mean([c for _, c, _, _, _ in paths])),
+           "c_abi_replay": replay_from_c(inst, paths, out),
            "what": "one branch length changed: 1 matrix, tip-to-root path of partials ops, root; host buffers, synchronous; "
                    "64 different paths in rotation (no plan-cache hits beyond the cache size); median"}
     return inc, run_incremental
