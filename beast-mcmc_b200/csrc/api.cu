@@ -157,7 +157,7 @@ void destroyInstance(Instance* in) {
     exchangeRelease(in);
     if (in->stream) cudaStreamSynchronize(in->stream);
     cudaFree(in->partialsBase); cudaFree(in->states8Base); cudaFree(in->states32Base);
-    for (CachedPlan& cp : in->planCache) { if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec); cudaFree(cp.dBlock); }
+    for (CachedPlan& cp : in->planCache) { cp.dropGraph(); cudaFree(cp.dBlock); }
     cudaFree(in->dEigen); cudaFree(in->dMat); cudaFree(in->dEvec); cudaFree(in->dIncSums); cudaFree(in->dIncCounter);
     if (in->hMapped) cudaFreeHost(in->hMapped); cudaFree(in->dRates); cudaFree(in->dWeights);
     cudaFree(in->dFreqs); cudaFree(in->dScale); cudaFree(in->dPatternWeights);
@@ -532,16 +532,23 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             const unsigned eigenGenNow = eigenSlot >= 0 ? in->eigenGen[eigenSlot] : 0u;
             // a captured graph carries the kernel choice and V / V^-1 by value: stale once the eigen system moved on
             if (cp.graphExec != nullptr && (cp.graphEigen != eigenSlot || cp.graphEigenGen != eigenGenNow)) {
-                cudaGraphExecDestroy(cp.graphExec);
-                cp.graphExec = nullptr;
-                cp.hits = 1;
-                if (++cp.graphInvalidations >= 4) cp.graphFailed = true;     // a model that moves every step: plain launches
+                // same kernels, new V / V^-1 (a substitution-model move): patch the captured launches in place
+                if (cp.graphAllEigen && eigenSlot >= 0 && cp.graphEigen == eigenSlot &&
+                    updateWalk4EGraph(cp.graphExec, cp.graphKernelNodes, in->hEigen.data() + (size_t)eigenSlot * 36) == cudaSuccess) {
+                    cp.graphEigenGen = eigenGenNow;
+                } else {
+                    cudaGetLastError();
+                    cp.dropGraph();
+                    cp.hits = 1;
+                    if (++cp.graphInvalidations >= 4) cp.graphFailed = true;     // the kernel choice flips every step: plain launches
+                }
             }
             // A plan that keeps coming back and needs several dependent launches is replayed as ONE graph launch:
             // on small alignments the host-side launch cost, not the kernels, sets the pace.
             int launches = 0;
             for (size_t ph = 0; ph + 1 < cp.phaseStart.size(); ++ph) launches += cp.phaseStart[ph + 1] > cp.phaseStart[ph];
-            if (in->useGraphs && launches >= 2) {
+            // (in-list cumulative scaling stages its index lists per call: those plans keep the plain launches)
+            if (in->useGraphs && launches >= 2 && cp.cumGroups.empty()) {
                 if (cp.graphExec == nullptr && !cp.graphFailed && cp.hits >= 2 && !in->timing &&
                     cudaStreamBeginCapture(in->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                     const cudaError_t e1 = launchPlan(in, cp.dBlock, static_cast<char*>(cp.dBlock) + cp.subsOffset, cp.phaseStart,
@@ -555,8 +562,23 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
                         cudaGraphInstantiate(&cp.graphExec, g, 0) != cudaSuccess) {
                         cp.graphExec = nullptr;
                         cp.graphFailed = true;
+                        if (g) cudaGraphDestroy(g);
+                    } else {
+                        cp.graph = g;
+                        cp.graphKernelNodes.clear();
+                        cp.graphAllEigen = cp.fourPath && eigenSlot >= 0 && !cp.preOrder;
+                        for (int dpt : cp.phaseDepth) cp.graphAllEigen = cp.graphAllEigen && dpt == 0;
+                        size_t nn = 0;
+                        if (cudaGraphGetNodes(g, nullptr, &nn) == cudaSuccess && nn > 0) {
+                            std::vector<cudaGraphNode_t> nodes(nn);
+                            cudaGraphNodeType ty;
+                            if (cudaGraphGetNodes(g, nodes.data(), &nn) == cudaSuccess)
+                                for (size_t q = 0; q < nn; ++q)
+                                    if (cudaGraphNodeGetType(nodes[q], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel)
+                                        cp.graphKernelNodes.push_back(nodes[q]);
+                        }
+                        if (cp.graphKernelNodes.empty()) cp.graphAllEigen = false;
                     }
-                    if (g) cudaGraphDestroy(g);
                     cudaGetLastError();
                 }
                 if (cp.graphExec != nullptr) {
@@ -851,7 +873,7 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
         }
         const size_t subsOffset = (opBytes + 255) & ~size_t(255);
         const size_t need = subsOffset + subBytes;
-        if (slot->graphExec) { cudaGraphExecDestroy(slot->graphExec); slot->graphExec = nullptr; }
+        slot->dropGraph();
         slot->hits = 0;
         slot->graphFailed = false;
         slot->graphInvalidations = 0;
@@ -1093,6 +1115,9 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&in->hOut), 1024 * sizeof(double)) == cudaSuccess;
     if (ok) {
         // default: one rate category set of all ones, unit pattern weights (upstream defaults)
+        in->hRates.assign((size_t)in->nSets * in->C, 1.0);
+        in->hWeights.assign((size_t)in->nSets * in->C, 0.0);
+        in->hFreqs.assign((size_t)in->nSets * 4, 0.0);
         std::vector<double> ones((size_t)std::max(in->nSets * in->C, in->Ppad), 1.0);
         ok = cudaMemcpyAsync(in->dRates, ones.data(), sizeof(double) * in->nSets * in->C, cudaMemcpyHostToDevice,
                              in->stream) == cudaSuccess;
@@ -1288,6 +1313,8 @@ int beagleSetStateFrequencies(int instance, int stateFrequenciesIndex, const dou
     if (!validRange(stateFrequenciesIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
     std::vector<double> f(in->Sp, 0.0);
     memcpy(f.data(), inStateFrequencies, sizeof(double) * in->S);
+    if (in->hFreqs.size() == (size_t)in->nSets * 4 && in->S <= 4)          // host mirror: travels by value in the fused launch
+        for (int i = 0; i < 4; ++i) in->hFreqs[(size_t)stateFrequenciesIndex * 4 + i] = i < in->S ? inStateFrequencies[i] : 0.0;
     return uploadSmall(in, in->dFreqs + (size_t)stateFrequenciesIndex * in->Sp, f.data(), sizeof(double) * in->Sp);
 }
 
@@ -1295,6 +1322,7 @@ int beagleSetCategoryWeights(int instance, int categoryWeightsIndex, const doubl
     SH(instance, shBroadcast(sh, [&](int c) { return beagleSetCategoryWeights(c, categoryWeightsIndex, inCategoryWeights); }));
     GET_INSTANCE(in, instance);
     if (!validRange(categoryWeightsIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::copy(inCategoryWeights, inCategoryWeights + in->C, in->hWeights.begin() + (size_t)categoryWeightsIndex * in->C);
     return uploadSmall(in, in->dWeights + (size_t)categoryWeightsIndex * in->C, inCategoryWeights, sizeof(double) * in->C);
 }
 
@@ -1302,6 +1330,7 @@ int beagleSetCategoryRatesWithIndex(int instance, int categoryRatesIndex, const 
     SH(instance, shBroadcast(sh, [&](int c) { return beagleSetCategoryRatesWithIndex(c, categoryRatesIndex, inCategoryRates); }));
     GET_INSTANCE(in, instance);
     if (!validRange(categoryRatesIndex, in->nSets)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::copy(inCategoryRates, inCategoryRates + in->C, in->hRates.begin() + (size_t)categoryRatesIndex * in->C);
     return uploadSmall(in, in->dRates + (size_t)categoryRatesIndex * in->C, inCategoryRates, sizeof(double) * in->C);
 }
 
@@ -1409,7 +1438,7 @@ int launchFused(Instance* in, int E, int wIdx, int fIdx, int cum, double* outSum
     IncArgs A;
     memset(&A, 0, sizeof A);
     A.partials = in->partialsBase; A.stride = in->partialsElems; A.states = in->states8Base; A.mats = in->dMat;
-    A.evecs = in->dEvec; A.scale = in->dScale; A.rates = in->dRates; A.matStride = in->matStride;
+    A.evecs = in->dEvec; A.scale = in->dScale; A.matStride = in->matStride;
     A.S = in->S; A.C = in->C; A.Ppad = in->Ppad; A.P = in->P; A.logScalers = in->logScalers ? 1 : 0;
     const double* h = in->hEigen.data() + (size_t)E * 36;
     for (int q = 0; q < 16; ++q) { A.V[q] = h[q]; A.Vi[q] = h[16 + q]; }
@@ -1418,6 +1447,7 @@ int launchFused(Instance* in, int E, int wIdx, int fIdx, int cum, double* outSum
     std::unordered_map<int, int> pendingOf;
     for (int q = 0; q < A.nMats; ++q) {
         A.mat[q] = IncMat{in->pendingMats[q].prob, in->pendingMats[q].rateSet, in->pendingMats[q].len};
+        for (int c = 0; c < 8; ++c) A.rate[q][c] = c < in->C ? in->hRates[(size_t)in->pendingMats[q].rateSet * in->C + c] : 0.0;
         pendingOf[in->pendingMats[q].prob] = q;
     }
     A.nOps = (int)in->pendingOps.size();
@@ -1439,8 +1469,8 @@ int launchFused(Instance* in, int E, int wIdx, int fIdx, int cum, double* outSum
         d.sw = o.sw; d.sr = o.sw >= 0 ? -1 : o.sr;
         prevDest = o.dest;
     }
-    A.weights = in->dWeights + (size_t)wIdx * in->C;
-    A.freqs = in->dFreqs + (size_t)fIdx * in->Sp;
+    for (int c = 0; c < 8; ++c) A.weights[c] = c < in->C ? in->hWeights[(size_t)wIdx * in->C + c] : 0.0;
+    for (int i = 0; i < 4; ++i) A.freqs[i] = in->hFreqs[(size_t)fIdx * 4 + i];
     A.cum = cum == BEAGLE_OP_NONE ? nullptr : in->dScale + (size_t)cum * in->Ppad;
     A.patternWeights = in->dPatternWeights; A.site = in->dSite; A.blockSums = in->dIncSums; A.counter = in->dIncCounter;
     A.out = in->dOut;
@@ -1665,6 +1695,13 @@ int beagleUpdatePartials(int instance, const BeagleOperation* operations, int op
         bool ok = true;
         for (const HostOp& o : hops)
             ok = ok && validRange(o.m1, in->nMatrices) && validRange(o.m2, in->nMatrices);
+        // The one-launch route runs the list as ONE dependent chain per pattern: right for what a move leaves dirty (one or two
+        // root paths: every op consumes its predecessor's result), wrong for a short list with subtree parallelism (the whole
+        // evaluation of a 62-taxon tree is 61 ops: the planned subtree walks finish it in a third of the time)
+        int breaks = 0;
+        for (int k = 1; k < operationCount; ++k)
+            breaks += hops[k].c1 != hops[k - 1].dest && hops[k].c2 != hops[k - 1].dest;
+        ok = ok && (breaks <= 2 || operationCount <= 16);
         const int E = ok ? eigenFormSlot(in, hops) : -1;
         for (const Instance::PendingMat& pm : in->pendingMats) ok = ok && pm.eigen == E;
         if (ok && E >= 0) {

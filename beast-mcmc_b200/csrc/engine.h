@@ -74,6 +74,16 @@ struct CachedPlan {
     int graphEigen = -2;                      // eigen slot / generation the captured launches carry by value (-1: matrix form)
     unsigned graphEigenGen = 0;
     int graphInvalidations = 0;
+    // kept for in-place updates: when only the CONTENT of the eigen system moved (a substitution-model move), the captured
+    // eigen-form walk launches get new V / V^-1 through cudaGraphExecKernelNodeSetParams instead of a re-capture
+    cudaGraph_t graph = nullptr;
+    std::vector<cudaGraphNode_t> graphKernelNodes;
+    bool graphAllEigen = false;
+    void dropGraph() {
+        if (graphExec) cudaGraphExecDestroy(graphExec);
+        if (graph) cudaGraphDestroy(graph);
+        graphExec = nullptr; graph = nullptr; graphKernelNodes.clear(); graphAllEigen = false;
+    }
 };
 
 enum TimingClass { T_PARTIALS = 0, T_MATRICES = 1, T_ROOT = 2, T_CLASSES = 3 };
@@ -84,11 +94,12 @@ constexpr int kIncMaxOps = 64, kIncMaxMats = 8;
 struct IncOp { int dest, c1, c2, m1, m2, sw, sr, flags; };      // m < 0: pending branch -(q+1); flags bit 0: c1 = previous result
 struct IncMat { int prob, rateSet; double len; };
 struct IncArgs {
-    double* partials; size_t stride; const uint8_t* states; double* mats; double* evecs; double* scale; const double* rates;
+    double* partials; size_t stride; const uint8_t* states; double* mats; double* evecs; double* scale;
     size_t matStride;
     int S, C, Ppad, P, logScalers, nOps, nMats, pad_;
     double V[16], Vi[16], eval[4];
-    const double* weights; const double* freqs; const double* cum; const double* patternWeights;
+    double weights[8], freqs[4], rate[kIncMaxMats][8];       // by value (host mirrors): no dependent load before the first flop
+    const double* cum; const double* patternWeights;
     double* site; double* blockSums; unsigned int* counter; double* out;
     volatile double* hostOut; volatile unsigned long long* hostFlag; unsigned long long seq;
     IncMat mat[kIncMaxMats];
@@ -146,6 +157,7 @@ struct Instance {
     int eigenWalk = 1;                        // B200_EIGEN_WALK: 0 = always the matrix-form kernel
     int tipMode = 2;                          // B200_TIP_MODE: compact tips by contraction (0), P column from global (1), shared-memory column table (2)
     double* dRates = nullptr;                 // [nSets][C]
+    std::vector<double> hRates, hWeights, hFreqs;   // host mirrors ([nSets][C], [nSets][C], [nSets][4]; 4-state instances use them)
     double* dWeights = nullptr;               // [nSets][C]
     double* dFreqs = nullptr;                 // [nSets][Sp]
     double* dScale = nullptr;                 // [nScale][Ppad]
@@ -236,6 +248,8 @@ cudaError_t launchTransitionMatrices(Instance* in, const int* dProbIdx, const in
 // dSubs[k] = (first op, one-past-last op, first pattern, one-past-last pattern) of subtree walk k
 cudaError_t launchWalk4(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int stackDepth, int maxWindow, bool preOrder);
 // walk4e.cu: eigen-form 4-state walk; eigen = [V (16) | V^-1 (16)]; aligned = every op covers [0, Ppad)
+// new V | V^-1 (32 doubles) for the captured eigen-form walk launches of a graph; any failure = the caller re-captures
+cudaError_t updateWalk4EGraph(cudaGraphExec_t exec, const std::vector<cudaGraphNode_t>& kernelNodes, const double* eigen);
 cudaError_t launchWalk4E(Instance* in, const Op4* dOps, const int4* dSubs, int nSubs, int maxWindow, bool aligned,
                          const double* eigen);
 cudaError_t launchWalkGeneric(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow, bool preOrder);

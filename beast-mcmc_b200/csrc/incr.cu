@@ -35,10 +35,39 @@ k_incremental(const IncArgs A) {
     __shared__ bool last;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int S = A.S, C = A.C;
+    const int c = lane / G;
+    const int p = blockIdx.x * (4 * G) + wib * G + (lane % G);
+    const bool catValid = c < C;
+    const int cc = catValid ? c : 0;
+    const bool inRange = p < A.Ppad;
+    const int pp = inRange ? p : 0;
+    const size_t off0 = ((size_t)cc * A.Ppad + pp) * 4;
+    // everything the chain will read from memory is known up front (the list is in the kernel parameters): start all of it
+    // on its way to L1 FIRST, so that the HBM/L2 latency of the siblings' partials overlaps the matrix prelude below and the
+    // dependent chain runs at cache-hit latency instead of one memory round trip per op
+    for (int k = 0; k < A.nOps; ++k) {
+        const IncOp op = A.op[k];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int child = ch == 0 ? op.c1 : op.c2, m = ch == 0 ? op.m1 : op.m2;
+            if (child < 0) {
+                if (c == 0) prefetchL1(A.states + (size_t)(-child - 1) * A.Ppad + pp);
+                if (m >= 0 && lane < 4) prefetchL1(A.mats + (size_t)m * A.matStride + lane * 4 * CP);
+            } else {
+                if (!(ch == 0 && (op.flags & 1)) && catValid) prefetchL1(A.partials + (size_t)child * A.stride + off0);
+                if (m >= 0 && lane == 0) prefetchL1(A.evecs + (size_t)m * CP * 4);
+            }
+        }
+        if (op.sr >= 0 && c == 0) prefetchL1(A.scale + (size_t)op.sr * A.Ppad + pp);
+    }
+    if (c == 0) {
+        prefetchL1(A.patternWeights + pp);
+        if (A.cum != nullptr) prefetchL1(A.cum + pp);
+    }
     // ---- 0. pending branches: spectra, then P = | V diag(e) V^-1 | with the reference's summation order
     for (int idx = tid; idx < A.nMats * C * 4; idx += 128) {
         const int q = idx / (C * 4), c = (idx >> 2) % C, k = idx & 3;
-        sE[q][c][k] = k < S ? exp(A.eval[k] * A.rates[(size_t)A.mat[q].rateSet * C + c] * A.mat[q].len) : 0.0;
+        sE[q][c][k] = k < S ? exp(A.eval[k] * A.rate[q][c] * A.mat[q].len) : 0.0;
     }
     __syncthreads();
     for (int idx = tid; idx < A.nMats * C * 16; idx += 128) {
@@ -65,30 +94,6 @@ k_incremental(const IncArgs A) {
     __syncthreads();
 
     // ---- 1. the list
-    const int c = lane / G;
-    const int p = blockIdx.x * (4 * G) + wib * G + (lane % G);
-    const bool catValid = c < C;
-    const int cc = catValid ? c : 0;
-    const bool inRange = p < A.Ppad;
-    const int pp = inRange ? p : 0;
-    const size_t off0 = ((size_t)cc * A.Ppad + pp) * 4;
-    // everything the chain will read from memory is known up front (the list is in the kernel parameters): start all of it
-    // on its way to L1 now, so that the dependent chain below runs at cache-hit latency instead of one L2 round trip per op
-    for (int k = 0; k < A.nOps; ++k) {
-        const IncOp op = A.op[k];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            const int child = ch == 0 ? op.c1 : op.c2, m = ch == 0 ? op.m1 : op.m2;
-            if (child < 0) {
-                if (c == 0) prefetchL1(A.states + (size_t)(-child - 1) * A.Ppad + pp);
-                if (m >= 0 && lane < 4) prefetchL1(A.mats + (size_t)m * A.matStride + lane * 4 * CP);
-            } else {
-                if (!(ch == 0 && (op.flags & 1)) && catValid) prefetchL1(A.partials + (size_t)child * A.stride + off0);
-                if (m >= 0 && lane == 0) prefetchL1(A.evecs + (size_t)m * CP * 4);
-            }
-        }
-        if (op.sr >= 0 && c == 0) prefetchL1(A.scale + (size_t)op.sr * A.Ppad + pp);
-    }
     double d[4] = {0.0, 0.0, 0.0, 0.0};
     for (int k = 0; k < A.nOps; ++k) {
         const IncOp op = A.op[k];
@@ -150,7 +155,7 @@ k_incremental(const IncArgs A) {
 
     // ---- 2. root: site[p] = log(sum_c w_c sum_i pi_i root[c,p,i]) + cum[p]; out = sum_p weight[p] site[p]
     double t = 0.0;
-    if (catValid) t = A.weights[c] * (A.freqs[0] * d[0] + A.freqs[1] * d[1] + A.freqs[2] * d[2] + A.freqs[3] * d[3]);
+    if (catValid) t = A.weights[cc] * (A.freqs[0] * d[0] + A.freqs[1] * d[1] + A.freqs[2] * d[2] + A.freqs[3] * d[3]);
 #pragma unroll
     for (int sh = G; sh < 32; sh <<= 1) t += __shfl_xor_sync(0xffffffffu, t, sh);
     double contrib = 0.0;

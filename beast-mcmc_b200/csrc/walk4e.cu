@@ -512,4 +512,21 @@ cudaError_t launchWalk4E(Instance* in, const Op4* dOps, const int4* dSubs, int n
     }
 }
 
+cudaError_t updateWalk4EGraph(cudaGraphExec_t exec, const std::vector<cudaGraphNode_t>& kernelNodes, const double* eigen) {
+    for (cudaGraphNode_t node : kernelNodes) {
+        cudaKernelNodeParams kp;
+        cudaError_t e = cudaGraphKernelNodeGetParams(node, &kp);
+        if (e != cudaSuccess) return e;
+        if (kp.kernelParams == nullptr || kp.kernelParams[0] == nullptr) return cudaErrorInvalidValue;
+        WalkArgs A = *static_cast<const WalkArgs*>(kp.kernelParams[0]);       // every eigen-form walk kernel takes ONE WalkArgs
+        for (int q = 0; q < 16; ++q) { A.V[q] = eigen[q]; A.Vi[q] = eigen[16 + q]; }
+        void* args[1] = {&A};
+        kp.kernelParams = args;
+        kp.extra = nullptr;
+        e = cudaGraphExecKernelNodeSetParams(exec, node, &kp);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace b200

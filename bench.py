@@ -488,6 +488,7 @@ def measure_single_partition(D, lib, beagle, w, tree, pats, model, site, steps, 
         res["kernels"] = [inst.getKernelTiming(c) for c in range(3)]
         inst.setKernelTiming(False)
     res["e2e"] = timed_e2e(D, step_e2e, e2e_steps or max(steps, 100))
+    res["e2e"]["c_abi_replay"] = full_evaluations_from_c(inst, ev, min(e2e_steps or max(steps, 100), 400)) if D.world == 1 else None
     return res
 
 
@@ -524,6 +525,37 @@ def replay_from_c(inst, paths, out):
     return {"us_per_eval": 1e6 * per[len(per) // 2], "us_p10": 1e6 * per[len(per) // 10], "us_p90": 1e6 * per[(9 * len(per)) // 10],
             "evals_per_s": 1.0 / per[len(per) // 2], "same_value_as_python_calls": bool(expect[0] == last.value),
             "what": "the same evaluations, the three C-ABI calls issued from C (harness/cdriver.c): no interpreter between calls"}
+
+
+def full_evaluations_from_c(inst, ev, steps):
+    """issue_sync's call sequence issued from C (harness/cdriver.c): the same host buffers go up, the same double comes down,
+    but no interpreter / ctypes marshalling between the nine calls -- what a JVM's JNI thread would see."""
+    import ctypes as C
+    lib_file = os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness", "libcdriver.so")
+    if not os.path.exists(lib_file):
+        return None
+    drv = C.CDLL(lib_file)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    ops2, prob2, scale2 = i32(np.concatenate(ev.ops)), i32(np.concatenate(ev.probIdx)), i32(np.concatenate(ev.scaleIdx))
+    root2, cum2 = i32(ev.rootIdx), i32(ev.cumIdx)
+    evec, ievc, evl = f64(ev.eig.Evec), f64(ev.eig.Ievc), f64(ev.eig.Eval)
+    rates, wts, frq = f64(ev.site.getCategoryRates()), f64(ev.site.getCategoryProportions()), f64(ev.model.getFrequencies())
+    lengths = f64(ev.lengths)
+    secs = np.zeros(steps + 10)
+    last = C.c_double(0.0)
+    pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    drv.cdriver_full_evaluations.restype = C.c_int
+    rc = drv.cdriver_full_evaluations(C.c_int(inst.instance), C.c_int(steps + 10), C.c_int(len(frq)), C.c_int(len(ev.nodeOps)), pi(ops2),
+                                      C.c_int(len(lengths)), pi(prob2), pd(lengths), pi(root2), pd(evec), pd(ievc), pd(evl), pd(rates),
+                                      pd(wts), pd(frq), C.c_int(1 if ev.scaling else 0), pi(scale2), pi(cum2), pd(secs), C.byref(last))
+    if rc != 0:
+        return {"error": rc}
+    per = sorted(secs[10:])
+    return {"value": 1.0 / per[len(per) // 2], "unit": "evals/s", "ms_per_step": 1e3 * per[len(per) // 2],
+            "p10_ms": 1e3 * per[len(per) // 10], "p90_ms": 1e3 * per[(9 * len(per)) // 10], "logL": last.value, "steps": steps,
+            "what": "the same synchronous call sequence with the same host buffers, issued from C (harness/cdriver.c)"}
 
 
 def incremental_section(inst, ev, tree, out, steps):
@@ -841,7 +873,7 @@ def main():
         "roofline": roof,
         "e2e": {"value": world / e2e["median_s"], "unit": "evals/s", "ms_per_step": e2e["median_ms"],
                 "h2d_bytes_per_step": ev.h2d_bytes(S, C), "d2h_bytes_per_step": 8, "logL": e2e["logL"],
-                "steps": e2e["steps"], "statistic": "median step, max over ranks",
+                "steps": e2e["steps"], "statistic": "median step, max over ranks", "c_abi_replay": e2e.get("c_abi_replay"),
                 "per_call_rank0": {k: e2e[k] for k in ("p10_ms", "median_ms", "p90_ms")}},
         "gpu_launches": int(k_n + m_n + r_n),
         "clocks": clocks,

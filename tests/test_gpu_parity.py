@@ -535,3 +535,38 @@ def test_plan_cache_hits_and_invalidation():
     a, b, c = run("4"), run("0"), run("4", graphs="0")
     assert a == b == c, (a, b, c)
     assert len(set(a[:10])) == 1 and a[12] == a[0] and a[11] != a[0]
+
+
+def test_graph_replay_follows_substitution_model_moves():
+    """A cached plan replayed as a CUDA graph carries V / V^-1 of the list's eigen system BY VALUE in its kernel nodes.  When
+    the substitution model moves (new eigen decomposition, same operation list) the captured launches must be patched
+    (cudaGraphExecKernelNodeSetParams) or re-captured -- never replayed stale.  Checked against the oracle driven by the same
+    calls, and bit-equal to the same engine without graphs."""
+    import os
+
+    def run(graphs):
+        tree, pats, model, site = H.synthetic_case(90, 300, 4, seed=78)      # > 64 operations: planned lists
+        os.environ["B200_GRAPHS"] = graphs
+        try:
+            g, o = _pair(tree, pats, model, site, rescalingScheme=S_.NONE)
+        finally:
+            os.environ.pop("B200_GRAPHS", None)
+        like_g, like_o = tdl.TreeDataLikelihood(g, tree), tdl.TreeDataLikelihood(o, tree)
+        out = []
+        for step in range(24):
+            if step >= 6 and step % 3 != 2:                 # two moves, one repeat, ...
+                model.rates = model.rates.copy()
+                model.rates[1] = 2.0 + 0.37 * step          # the A<->G rate: a new eigen system, same lists
+                model.rates[4] = 3.0 + 0.11 * step
+                model._eigen = None
+            for like in (like_g, like_o):
+                like.makeDirty()
+            vg, vo = like_g.getLogLikelihood(), like_o.getLogLikelihood()
+            assert _rel(vg, vo) <= REL, (step, vg, vo)
+            out.append(vg)
+        g.finalize()
+        return out
+
+    a, b = run("1"), run("0")
+    assert a == b
+    assert len(set(a)) > 10
