@@ -835,6 +835,24 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             }
         }
     }
+    if (fourPath && !preOrder) {
+        // bits 2 / 3 of pad_: child 1 / 2 is a partials buffer NOT written by this walk, i.e. final in memory when the walk
+        // starts -- a short walk (a latency chain near the root) starts all of them on their way to L1 up front
+        std::unordered_map<int, int> writerSub;
+        for (size_t sIdx = 0; sIdx < plan.subs.size(); ++sIdx)
+            for (int pos = plan.subs[sIdx].begin; pos < plan.subs[sIdx].end; ++pos) writerSub[ops4[pos].dest] = (int)sIdx;
+        for (size_t sIdx = 0; sIdx < plan.subs.size(); ++sIdx)
+            for (int pos = plan.subs[sIdx].begin; pos < plan.subs[sIdx].end; ++pos) {
+                Op4& d = ops4[pos];
+                auto outside = [&](int child) {
+                    if (child < 0) return false;
+                    auto it = writerSub.find(child);
+                    return it == writerSub.end() || it->second != (int)sIdx;
+                };
+                if (outside(d.c1)) d.pad_ |= 4;
+                if (outside(d.c2)) d.pad_ |= 8;
+            }
+    }
     if (fourPath && getenv("B200_BEAGLE_DEBUG")) {
         int fwd = 0, internal = 0;
         for (const Op4& d : ops4) { fwd += (d.pad_ & 2) != 0; internal += (d.c1 >= 0) + (d.c2 >= 0); }
