@@ -835,24 +835,6 @@ int planAndLaunch(Instance* in, const std::vector<HostOp>& hops, bool byPartitio
             }
         }
     }
-    if (fourPath && !preOrder) {
-        // bits 2 / 3 of pad_: child 1 / 2 is a partials buffer NOT written by this walk, i.e. final in memory when the walk
-        // starts -- a short walk (a latency chain near the root) starts all of them on their way to L1 up front
-        std::unordered_map<int, int> writerSub;
-        for (size_t sIdx = 0; sIdx < plan.subs.size(); ++sIdx)
-            for (int pos = plan.subs[sIdx].begin; pos < plan.subs[sIdx].end; ++pos) writerSub[ops4[pos].dest] = (int)sIdx;
-        for (size_t sIdx = 0; sIdx < plan.subs.size(); ++sIdx)
-            for (int pos = plan.subs[sIdx].begin; pos < plan.subs[sIdx].end; ++pos) {
-                Op4& d = ops4[pos];
-                auto outside = [&](int child) {
-                    if (child < 0) return false;
-                    auto it = writerSub.find(child);
-                    return it == writerSub.end() || it->second != (int)sIdx;
-                };
-                if (outside(d.c1)) d.pad_ |= 4;
-                if (outside(d.c2)) d.pad_ |= 8;
-            }
-    }
     if (fourPath && getenv("B200_BEAGLE_DEBUG")) {
         int fwd = 0, internal = 0;
         for (const Op4& d : ops4) { fwd += (d.pad_ & 2) != 0; internal += (d.c1 >= 0) + (d.c2 >= 0); }
@@ -1066,9 +1048,10 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->walkR = envInt("B200_WALK_R", 4);
     if (in->walkR != 1 && in->walkR != 2 && in->walkR != 4 && in->walkR != 8) in->walkR = 4;
     if (getenv("B200_WALK_R") == nullptr && in->matCP > 0) {
-        // patterns per thread: as many as still leave >= 2 warps per SM inside ONE subtree walk
+        // patterns per thread: as many as still leave >= 1 warp per SM inside ONE subtree walk (the phases supply the rest of
+        // the parallelism: measured on the 6000-pattern Makona-like set, 25 subtrees per launch: R = 4 0.273 ms, R = 2 0.340 ms)
         const int G = 32 / in->matCP;
-        while (in->walkR > 1 && (in->Ppad + G * in->walkR - 1) / (G * in->walkR) < 2 * in->smCount) in->walkR >>= 1;
+        while (in->walkR > 1 && (in->Ppad + G * in->walkR - 1) / (G * in->walkR) < in->smCount) in->walkR >>= 1;
     }
     in->stackDepthMax = std::min(64, std::max(0, envInt("B200_STACK_DEPTH", 12)));
 

@@ -212,7 +212,7 @@ struct Instance {
     long timedLaunches[T_CLASSES] = {0, 0, 0};
 
     // tuning knobs (environment overridable, see api.cu)
-    size_t walkSmemConfigured = 0, genericSmemConfigured = 0, mmaSmemConfigured[4] = {0, 0, 0, 0};
+    size_t walkSmemConfigured = 0, genericSmemConfigured = 0, mmaSmemConfigured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int walkBlock = 128;
     int walkVariant = 0;
     std::vector<CachedPlan> planCache;

@@ -840,9 +840,12 @@ __device__ __forceinline__ void bulkCopyG2S(void* smemDst, const void* gmemSrc, 
 // the matrices sit in global memory already in the padded [Sp][Sp+4] shape the fragment loads want, so each is one
 // contiguous transfer; everyone else waits on the mbarrier and spends no issue slots on staging.  Single buffer: the
 // other resident blocks of the SM cover the copy (measured faster than a double buffer at one block per SM).
-template <int NT, int WARPS, bool PRE, bool MULTI>
+// MT = 8-pattern m-tiles per warp: 2 where the launch fills the GPU (each B fragment feeds two DMMAs), 1 for the thin phases near
+// the root, where twice as many (half as tall) blocks put every SM to work
+template <int NT, int WARPS, bool PRE, bool MULTI, int MT = 2>
 __global__ void __launch_bounds__(WARPS * 32, 3)
 k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, int C, int Ppad, int logScalers, int cbArg) {
+    static_assert(MT == 2 || (MT == 1 && !PRE), "the pre-order form keeps two m-tiles per warp");
     const int cb = MULTI ? cbArg : 1;               // MULTI = false: one category per staging round, folded at compile time
     constexpr int Sp = 8 * NT;
     constexpr int LD = Sp + 4;                       // shared-memory row stride (doubles)
@@ -855,8 +858,8 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int4 range = subs[blockIdx.y];
-    if (range.z + blockIdx.x * (WARPS * 16) >= range.w) return;      // block outside this subtree's pattern window
-    const int pw = range.z + blockIdx.x * (WARPS * 16) + w * 16;      // first pattern of this warp's 16-row tile
+    if (range.z + blockIdx.x * (WARPS * 8 * MT) >= range.w) return;  // block outside this subtree's pattern window
+    const int pw = range.z + blockIdx.x * (WARPS * 8 * MT) + w * 8 * MT;   // first pattern of this warp's (8 MT)-row tile
     const size_t mRow = (size_t)C * Sp * Sp;         // offset of the padded row-major copies in a matrix buffer
     const size_t mTp = mRow + (size_t)C * MATSZ;     // offset of the padded transposed copies
     const int total = (range.y - range.x) * C;
@@ -867,13 +870,15 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
     __syncthreads();
     unsigned parity = 0;
 
-    bool act[2] = {false, false};
-    double rowMax[2] = {0.0, 0.0};
+    bool act[MT];
+    double rowMax[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { act[m] = false; rowMax[m] = 0.0; }
     // the accumulator tile outlives the iteration: with one category the next op of the walk may take it as its first
     // child straight from these registers (DevOp::pad_ bit 1, set by the planner as for the 4-state walk)
-    double acc[2][NT][2];
+    double acc[MT][NT][2];
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
         for (int n = 0; n < NT; ++n) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
     for (int flat = 0; flat < total; ++flat) {
@@ -901,7 +906,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
         const double* P2 = smw + (size_t)(cb + cg) * MATSZ;
         if (c == 0) {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
+            for (int m = 0; m < MT; ++m) {
                 const int p = pw + 8 * m + g;
                 act[m] = p < range.w && p >= op.pBegin && p < op.pEnd;
                 rowMax[m] = 0.0;
@@ -981,10 +986,10 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
         for (int child = 0; child < 2; ++child) {
             const double* xg = child == 0 ? op.c1 : op.c2;
             const double* Ps = child == 0 ? P1 : P2;
-            double cur[2][NT][2];
+            double cur[MT][NT][2];
             if (xg != nullptr) {
 #pragma unroll
-                for (int m = 0; m < 2; ++m)
+                for (int m = 0; m < MT; ++m)
 #pragma unroll
                     for (int n = 0; n < NT; ++n) { cur[m][n][0] = 0.0; cur[m][n][1] = 0.0; }
                 // The sum over the child's states j may visit them in any order, so k-chunk (n, e0) is DEFINED as the four
@@ -994,40 +999,47 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 // A operands ARE the accumulator registers (no shuffle, no memory), with the same arithmetic either way.
                 const bool fwd = child == 0 && C == 1 && (op.pad_ & 2) != 0;
                 const int flip = t >> 1;
-                const double* xrow0 = xg + ((size_t)c * Ppad + (pw + g)) * Sp + 2 * t;
-                const double* xrow1 = xrow0 + (size_t)8 * Sp;
+                const double* xrow = xg + ((size_t)c * Ppad + (pw + g)) * Sp + 2 * t;      // m-tile m: + m * 8 rows
                 const double* brow = Ps + g * LD + 2 * t;
-                const bool ld0 = act[0] && !fwd, ld1 = act[1] && !fwd;
-                double2 x0 = make_double2(0.0, 0.0), x1 = make_double2(0.0, 0.0);
-                if (ld0) x0 = *reinterpret_cast<const double2*>(xrow0);
-                if (ld1) x1 = *reinterpret_cast<const double2*>(xrow1);
+                bool ld[MT];
+                double2 x[MT];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    ld[m] = act[m] && !fwd;
+                    x[m] = make_double2(0.0, 0.0);
+                    if (ld[m]) x[m] = *reinterpret_cast<const double2*>(xrow + (size_t)m * 8 * Sp);
+                }
 #pragma unroll
                 for (int n = 0; n < NT; ++n) {
-                    double2 nx0 = make_double2(0.0, 0.0), nx1 = make_double2(0.0, 0.0);
-                    if (n + 1 < NT) {                                        // the next state pair travels while this one computes
-                        if (ld0) nx0 = *reinterpret_cast<const double2*>(xrow0 + 8 * (n + 1));
-                        if (ld1) nx1 = *reinterpret_cast<const double2*>(xrow1 + 8 * (n + 1));
+                    double2 nx[MT];
+                    double v[MT][2];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        nx[m] = make_double2(0.0, 0.0);                     // the next state pair travels while this one computes
+                        if (n + 1 < NT && ld[m]) nx[m] = *reinterpret_cast<const double2*>(xrow + (size_t)m * 8 * Sp + 8 * (n + 1));
+                        v[m][0] = fwd ? acc[m][n][0] : x[m].x;
+                        v[m][1] = fwd ? acc[m][n][1] : x[m].y;
                     }
-                    const double v00 = fwd ? acc[0][n][0] : x0.x, v01 = fwd ? acc[0][n][1] : x0.y;
-                    const double v10 = fwd ? acc[1][n][0] : x1.x, v11 = fwd ? acc[1][n][1] : x1.y;
 #pragma unroll
                     for (int e0 = 0; e0 < 2; ++e0) {
                         const int e = e0 ^ flip;
-                        const double a0 = e ? v01 : v00;
-                        const double a1 = e ? v11 : v10;
+                        double a[MT];
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) a[m] = e ? v[m][1] : v[m][0];
 #pragma unroll
                         for (int n2 = 0; n2 < NT; ++n2) {
                             const double b = brow[n2 * 8 * LD + 8 * n + e];
-                            dmma884acc(cur[0][n2][0], cur[0][n2][1], a0, b);
-                            dmma884acc(cur[1][n2][0], cur[1][n2][1], a1, b);
+#pragma unroll
+                            for (int m = 0; m < MT; ++m) dmma884acc(cur[m][n2][0], cur[m][n2][1], a[m], b);
                         }
                     }
-                    x0 = nx0; x1 = nx1;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) x[m] = nx[m];
                 }
             } else {
                 const int* st = static_cast<const int*>(child == 0 ? op.s1 : op.s2);
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < MT; ++m) {
                     const int p = pw + 8 * m + g;
                     const int s = act[m] ? st[p] : S;
                     const double* col = Ps + (size_t)(s < S ? s : 0) * LD + 2 * t;      // staged TRANSPOSED: row s = column s of P
@@ -1040,7 +1052,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
                 }
             }
 #pragma unroll
-            for (int m = 0; m < 2; ++m)
+            for (int m = 0; m < MT; ++m)
 #pragma unroll
                 for (int n = 0; n < NT; ++n)
 #pragma unroll
@@ -1053,7 +1065,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
         const bool scaleInRegisters = C == 1 && (op.scaleWrite != nullptr || op.scaleRead != nullptr);
         if (scaleInRegisters) {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
+            for (int m = 0; m < MT; ++m) {
                 const int p = pw + 8 * m + g;
                 double f;
                 if (op.scaleWrite != nullptr) {
@@ -1077,7 +1089,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
         }
         // store the tile: lane (g,t) owns states 8n+2t, 8n+2t+1 of rows g and g+8
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
+        for (int m = 0; m < MT; ++m) {
             if (!act[m]) continue;
             double* drow = op.dest + ((size_t)c * Ppad + (pw + 8 * m + g)) * Sp + 2 * t;
 #pragma unroll
@@ -1090,7 +1102,7 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
             // per-pattern factor (max over categories and states), then one more pass over what this
             // warp just wrote (same lanes re-read their own stores)
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
+            for (int m = 0; m < MT; ++m) {
                 const int p = pw + 8 * m + g;
                 double f;
                 if (op.scaleWrite != nullptr) {
@@ -1126,28 +1138,35 @@ k_walk_mma(const DevOp* __restrict__ ops, const int4* __restrict__ subs, int S, 
     }
 }
 
-template <int NT, int WARPS, bool PRE = false>
+template <int NT, int WARPS, bool PRE = false, int MT = 2>
 static cudaError_t launchWalkMmaT(Instance* in, const DevOp* dOps, const int4* dSubs, int nSubs, int maxWindow) {
     constexpr int Sp = 8 * NT;
+    constexpr int TILE = WARPS * 8 * MT;             // patterns per block
     const size_t pair = 2 * (size_t)Sp * (Sp + 4) * sizeof(double);
     // as many categories per staging round as keep three blocks resident per SM (72 KB each)
     const int cb = (int)std::max<size_t>(1, std::min<size_t>((size_t)in->C, (72 * 1024) / pair));
     const size_t smem = pair * cb;
-    dim3 grid((maxWindow + WARPS * 16 - 1) / (WARPS * 16), nSubs);
+    dim3 grid((maxWindow + TILE - 1) / TILE, nSubs);
+    if constexpr (MT == 2) {
+        // a thin phase (the walks near the root: fewer blocks than two per SM) runs with 8-pattern warp tiles: twice the blocks
+        if (!PRE && (long)grid.x * nSubs < 2L * in->smCount && in->thinR1)
+            return launchWalkMmaT<NT, WARPS, PRE, PRE ? 2 : 1>(in, dOps, dSubs, nSubs, maxWindow);
+    }
+    const int slot = (PRE ? 1 : 0) + (MT == 1 ? 4 : 0);
     if (cb == 1) {
-        if (smem > in->mmaSmemConfigured[PRE ? 1 : 0]) {
-            cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, PRE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > in->mmaSmemConfigured[slot]) {
+            cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, PRE, false, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            in->mmaSmemConfigured[PRE ? 1 : 0] = smem;
+            in->mmaSmemConfigured[slot] = smem;
         }
-        k_walk_mma<NT, WARPS, PRE, false><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0, 1);
+        k_walk_mma<NT, WARPS, PRE, false, MT><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0, 1);
     } else {
-        if (smem > in->mmaSmemConfigured[PRE ? 3 : 2]) {
-            cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, PRE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > in->mmaSmemConfigured[slot + 2]) {
+            cudaError_t e = cudaFuncSetAttribute(k_walk_mma<NT, WARPS, PRE, true, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            in->mmaSmemConfigured[PRE ? 3 : 2] = smem;
+            in->mmaSmemConfigured[slot + 2] = smem;
         }
-        k_walk_mma<NT, WARPS, PRE, true><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0, cb);
+        k_walk_mma<NT, WARPS, PRE, true, MT><<<grid, WARPS * 32, smem, in->stream>>>(dOps, dSubs, in->S, in->C, in->Ppad, in->logScalers ? 1 : 0, cb);
     }
     return cudaGetLastError();
 }

@@ -325,25 +325,6 @@ k_walk4p(const WalkArgs A) {
         asm volatile("cp.async.commit_group;" ::: "memory");
         return Rec{rec.x, rec.y, rec.z, rec2.y, rec2.z, flags, pf.x, pf.y};
     };
-    // a short walk is a latency chain (the phases near the root): every child cell that is final in memory (not written by this
-    // walk: pad_ bits 2 / 3, set by the planner) starts its trip to L1 NOW, so that the chain below pays one memory latency in
-    // total instead of one per op.  Long walks rely on the one-op look-ahead (pfA / pfB) instead.
-    if (range.y - range.x <= 24 && catValid) {
-        for (int k = range.x; k <= last; ++k) {
-            const int4 rec = __ldg(reinterpret_cast<const int4*>(A.ops + k));             // dest, c1, c2, m1
-            const int flags = __ldg(&A.ops[k].pad_);
-            if ((flags & 4) && !(flags & 2)) {
-                const double* xg = A.partials + (size_t)rec.y * A.stride + off0;
-#pragma unroll
-                for (int r = 0; r < R; ++r) prefetchL1(xg + (size_t)r * G * 4);
-            }
-            if (flags & 8) {
-                const double* xg = A.partials + (size_t)rec.z * A.stride + off0;
-#pragma unroll
-                for (int r = 0; r < R; ++r) prefetchL1(xg + (size_t)r * G * 4);
-            }
-        }
-    }
     // prologue: records k0 (and k0+1 through issueOperands), then the operands of k0
     if (lane < 4) cpAsync16(reinterpret_cast<char*>(&ring[range.x & 3]) + 16 * lane,
                             reinterpret_cast<const char*>(A.ops + range.x) + 16 * lane);
