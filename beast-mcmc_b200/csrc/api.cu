@@ -1024,6 +1024,7 @@ int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBuffe
     in->hEigen.assign((size_t)std::max(1, in->nEigen) * 36, 0.0);
     in->eigenWalk = envInt("B200_EIGEN_WALK", 1);
     in->tipMode = envInt("B200_TIP_MODE", 3);
+    in->thinTipMode = envInt("B200_THIN_TIP_MODE", in->tipMode);
     in->walkBlock = 128;
     in->walkVariant = envInt("B200_WALK_VARIANT", 0);
     in->reorder = envInt("B200_REORDER", 1);

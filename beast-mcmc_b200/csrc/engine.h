@@ -156,6 +156,7 @@ struct Instance {
     std::vector<double> hEigen;               // [nEigen][32]: V | V^-1 padded to 4 x 4 (host copy, by value into the launch)
     int eigenWalk = 1;                        // B200_EIGEN_WALK: 0 = always the matrix-form kernel
     int tipMode = 2;                          // B200_TIP_MODE: compact tips by contraction (0), P column from global (1), shared-memory column table (2)
+    int thinTipMode = 3;                     // the same choice for thin (R = 1) phases (B200_THIN_TIP_MODE)
     double* dRates = nullptr;                 // [nSets][C]
     std::vector<double> hRates, hWeights, hFreqs;   // host mirrors ([nSets][C], [nSets][C], [nSets][4]; 4-state instances use them)
     double* dWeights = nullptr;               // [nSets][C]

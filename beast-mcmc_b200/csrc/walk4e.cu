@@ -445,7 +445,7 @@ cudaError_t launchR(Instance* in, WalkArgs& A, int nSubs, int maxWindow, bool al
     // predicate-free only when a warp's G*R patterns can never straddle the end of the padded pattern axis
     if (!aligned || in->Ppad % (G * R) != 0) return launchK<CP, R, false, 4, TIPD>(in, A, grid);
     if constexpr (CP <= 8 && G * R >= 4) {
-        if (in->tipMode == 3) {                 // per-warp asynchronous operand staging (k_walk4p)
+        if ((R == 1 ? in->thinTipMode : in->tipMode) == 3) {     // per-warp asynchronous operand staging (k_walk4p)
             if constexpr (CP == 4) {
                 // measured (profiles/r02_sweep_cfg2.txt): a launch bound of 3 blocks lets ptxas keep 120 registers without a
                 // spill and 4 blocks still fit -- the fastest setting unless B200_WALK_MINB says otherwise

@@ -316,8 +316,9 @@ BEAGLE_DLLEXPORT int b200GetKernelTiming(int instance, int which, double* outMil
  * string is the build-metadata suffix of beagleGetVersion ("4.0.1-b200+<hash>"). */
 BEAGLE_DLLEXPORT const char* b200GetSourceHash(void);
 /* Deferred small evaluations (csrc/incr.cu): on 4-state instances a short beagleUpdateTransitionMatrices (<= 8 branches) ->
- * beagleUpdatePartials (<= 64 operations) -> beagleCalculateRootLogLikelihoods sequence -- what an MCMC move that dirties
- * one root path issues (MarkovChain.java:207-393) -- is executed as ONE kernel launch at the root call, its result written
+ * beagleUpdatePartials (<= 64 operations, chain-like: every operation but at most two consumes its predecessor's result, or
+ * <= 16 operations) -> beagleCalculateRootLogLikelihoods sequence -- what an MCMC move that dirties one or two root paths
+ * issues (MarkovChain.java:207-393) -- is executed as ONE kernel launch at the root call, its result written
  * to mapped pinned host memory; any other entry point first launches what was deferred, so the calls keep their upstream
  * meaning.  B200_FUSE=0 (environment) switches the deferral off.  This counter reports how often it happened. */
 BEAGLE_DLLEXPORT long b200GetFusedLaunches(int instance);
